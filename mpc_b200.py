@@ -1,0 +1,12 @@
+"""Importable alias for the package directory `multi-purpose-mpc_b200/` (hyphens are not valid in a
+Python module name): `import mpc_b200` loads that directory as the package `mpc_b200`."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multi-purpose-mpc_b200")
+_spec = importlib.util.spec_from_file_location("mpc_b200", os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["mpc_b200"] = _mod
+_spec.loader.exec_module(_mod)

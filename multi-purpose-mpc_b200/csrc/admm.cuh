@@ -1,0 +1,672 @@
+// admm.cuh -- K1 (LTV assembly) + K2 (OSQP-equivalent ADMM) for sm_100a.
+//
+// One warp per scenario, one lane per horizon stage (N + 1 <= 32).  Lane j keeps the whole of
+// stage j of the QP that MPC._init_problem builds (reference: src/MPC.py:61-159) in registers:
+//   variables w_j = (e_y, e_psi, t, v, kappa)_j              (stage N has no inputs)
+//   rows      dynamics block j (3 equalities, MPC.py:128-131,142-147) + 5 bound rows (MPC.py:133)
+// The OSQP iteration (restated in oracle/osqp_oracle.c; executable model in
+// tools/admm_pcr_model.py) runs entirely in registers; neighbouring stages talk through warp
+// shuffles.  The reduced KKT system (P + sigma I + A' diag(rho) A) x = b is block tridiagonal over
+// stages: the two inputs of a stage are eliminated locally (their 2x2 block is diagonal), and the
+// remaining chain of 3x3 blocks is solved by parallel cyclic reduction (log2(32) = 5 levels), so
+// one linear solve is ~40 shuffles + ~130 FMAs per lane instead of a 31-step serial Riccati sweep.
+// Norms for termination / rho adaptation are warp reductions (redux.sync on the float bit pattern
+// for fp32).  No tensor cores: per-instance 3x3 / 5x5 blocks are not a dense contraction.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace mpcb {
+
+constexpr double kOsqpInfty = 1e30;
+constexpr double kMinScaling = 1e-4;
+constexpr double kMaxScaling = 1e4;
+constexpr double kRhoMin = 1e-6;
+constexpr double kRhoMax = 1e6;
+constexpr double kRhoEqOverIneq = 1e3;
+constexpr double kRhoTol = 1e-4;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct AdmmSettings {
+    double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, adaptive_rho_tolerance;
+    int max_iter, scaling, check_termination, adaptive_rho_interval, refine;
+};
+
+struct MpcParams {  // MPC.__init__ arguments (MPC.py:15-59) + car geometry
+    int N;
+    double Q[3], R[2], QN[3], xmin[3], xmax[3], umin[2], umax[2];
+    double ay_max, L;
+};
+
+struct PathView {  // device tables, one row per quantity (set by mpc_set_path)
+    int n_wp, circular;
+    const double *x, *y, *psi, *kappa, *v_ref, *ds_next, *cos_psi, *sin_psi, *cos_ub, *sin_ub, *cos_lb, *sin_lb;
+    const double *length_cum;
+    const double *border;  // [n_wp][4]
+};
+
+// ------------------------------------------------------------------------------------------------
+// warp helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T shfl_up(T v, int s) { return __shfl_up_sync(kFull, v, s); }
+template <typename T> __device__ __forceinline__ T shfl_dn(T v, int s) { return __shfl_down_sync(kFull, v, s); }
+
+__device__ __forceinline__ float warp_max(float v) {  // v >= 0: order of the bit pattern = order of the value
+    return __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(v)));
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, s));
+    return v;
+}
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(kFull, v, s);
+    return v;
+}
+template <typename T> __device__ __forceinline__ T tabs(T v) { return v < T(0) ? -v : v; }
+template <typename T> __device__ __forceinline__ T tmax(T a, T b) { return a > b ? a : b; }
+template <typename T> __device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
+__device__ __forceinline__ float trsqrt(float v) { return 1.0f / sqrtf(v); }
+__device__ __forceinline__ double trsqrt(double v) { return 1.0 / sqrt(v); }
+template <typename T> __device__ __forceinline__ T limit_scaling(T v) {
+    v = v < T(kMinScaling) ? T(1) : v;
+    return v > T(kMaxScaling) ? T(kMaxScaling) : v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-lane stage data
+// ------------------------------------------------------------------------------------------------
+// a[8]: nonzeros of [A_j B_j] (rows of dynamics block j+1, sbm.py:404-410):
+//   a0=A00 a1=A01 | a2=A10 a3=A11 a6=B11(kappa) | a4=A20 a5=A22 a7=B20(v)
+// c[3]: the -I entries of dynamics block j on x_j;  e[5]: identity (bound) rows.
+template <typename T> struct Stage {
+    T a[8], c[3], e[5];
+    T P[5], q[5];
+    T d[3];          // rhs of dynamics block j (l = u)
+    T lo[5], hi[5];  // bound rows
+    T D[5], Ed[3], Eb[5];
+    T cs;            // cost scaling c
+    int ctype[5];    // -1 loose, 0 inequality, 1 equality (bound rows; dynamics rows are always 1)
+};
+
+template <typename T, int NLEV> struct Factor {
+    T al[NLEV][9], be[NLEV][9];
+    T Dinv[6];             // symmetric: 00 01 02 11 12 22
+    T iv, ik;              // 1 / S_vv, 1 / S_kk
+    T sxv0, sxv2, sxk0, sxk1;  // S_xu nonzeros
+    T fv, fk;              // coupling of (v, kappa)_j to (t, e_psi)_{j+1}
+};
+
+// z = A w for this lane: zd (dynamics block j) and zb (bound rows)
+template <typename T>
+__device__ __forceinline__ void A_apply(const Stage<T>& s, const T w[5], int lane, T zd[3], T zb[5]) {
+    T o0 = s.a[0] * w[0] + s.a[1] * w[1];
+    T o1 = s.a[2] * w[0] + s.a[3] * w[1] + s.a[6] * w[4];
+    T o2 = s.a[4] * w[0] + s.a[5] * w[2] + s.a[7] * w[3];
+    o0 = shfl_up(o0, 1); o1 = shfl_up(o1, 1); o2 = shfl_up(o2, 1);
+    if (lane == 0) { o0 = T(0); o1 = T(0); o2 = T(0); }
+    zd[0] = s.c[0] * w[0] + o0; zd[1] = s.c[1] * w[1] + o1; zd[2] = s.c[2] * w[2] + o2;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) zb[i] = s.e[i] * w[i];
+}
+
+// r = A' y for this lane's 5 variables
+template <typename T>
+__device__ __forceinline__ void At_apply(const Stage<T>& s, const T yd[3], const T yb[5], T r[5]) {
+    T g0 = shfl_dn(yd[0], 1), g1 = shfl_dn(yd[1], 1), g2 = shfl_dn(yd[2], 1);
+    // lanes whose successor is outside the chain have a == 0, so the shuffled value is harmless
+    r[0] = s.c[0] * yd[0] + s.a[0] * g0 + s.a[2] * g1 + s.a[4] * g2 + s.e[0] * yb[0];
+    r[1] = s.c[1] * yd[1] + s.a[1] * g0 + s.a[3] * g1 + s.e[1] * yb[1];
+    r[2] = s.c[2] * yd[2] + s.a[5] * g2 + s.e[2] * yb[2];
+    r[3] = s.a[7] * g2 + s.e[3] * yb[3];
+    r[4] = s.a[6] * g1 + s.e[4] * yb[4];
+}
+
+// OSQP scale_data (Ruiz equilibration of the KKT matrix + cost scaling), stage layout.
+template <typename T>
+__device__ __forceinline__ void ruiz_scale(Stage<T>& s, int iters, int nvar) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { s.D[i] = T(1); s.Eb[i] = T(1); }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s.Ed[i] = T(1);
+    s.cs = T(1);
+    for (int it = 0; it < iters; ++it) {
+        T aa[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) aa[i] = tabs(s.a[i]);
+        T col[5];
+        col[0] = tmax(tmax(aa[0], aa[2]), aa[4]);
+        col[1] = tmax(aa[1], aa[3]);
+        col[2] = aa[5];
+        col[3] = aa[7];
+        col[4] = aa[6];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) col[i] = tmax(col[i], tabs(s.c[i]));
+#pragma unroll
+        for (int i = 0; i < 5; ++i) col[i] = tmax(tmax(col[i], tabs(s.e[i])), tabs(s.P[i]));
+        T ro[3];
+        ro[0] = tmax(aa[0], aa[1]);
+        ro[1] = tmax(tmax(aa[2], aa[3]), aa[6]);
+        ro[2] = tmax(tmax(aa[4], aa[5]), aa[7]);
+        const int lane = threadIdx.x & 31;
+        T Dt[5], Edt[3], Ebt[5];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            T r = shfl_up(ro[i], 1);
+            if (lane == 0) r = T(0);
+            Edt[i] = trsqrt(limit_scaling(tmax(tabs(s.c[i]), r)));
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            Dt[i] = trsqrt(limit_scaling(col[i]));
+            Ebt[i] = trsqrt(limit_scaling(tabs(s.e[i])));
+        }
+        T En[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) En[i] = shfl_dn(Edt[i], 1);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) s.P[i] = s.P[i] * Dt[i] * Dt[i];
+        s.a[0] = s.a[0] * En[0] * Dt[0]; s.a[1] = s.a[1] * En[0] * Dt[1];
+        s.a[2] = s.a[2] * En[1] * Dt[0]; s.a[3] = s.a[3] * En[1] * Dt[1];
+        s.a[4] = s.a[4] * En[2] * Dt[0]; s.a[5] = s.a[5] * En[2] * Dt[2];
+        s.a[6] = s.a[6] * En[1] * Dt[4]; s.a[7] = s.a[7] * En[2] * Dt[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { s.c[i] = s.c[i] * Edt[i] * Dt[i]; s.Ed[i] *= Edt[i]; }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            s.e[i] = s.e[i] * Ebt[i] * Dt[i];
+            s.q[i] *= Dt[i];
+            s.D[i] *= Dt[i];
+            s.Eb[i] *= Ebt[i];
+        }
+        // cost scaling
+        T sp = T(0), mq = T(0);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { sp += tabs(s.P[i]); mq = tmax(mq, tabs(s.q[i])); }
+        sp = warp_sum(sp) / T(nvar);
+        mq = limit_scaling(warp_max(mq));
+        T ct = limit_scaling(tmax(sp, mq));
+        ct = T(1) / ct;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { s.P[i] *= ct; s.q[i] *= ct; }
+        s.cs *= ct;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s.d[i] *= s.Ed[i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { s.lo[i] *= s.Eb[i]; s.hi[i] *= s.Eb[i]; }
+}
+
+// 3x3 helpers (row-major)
+template <typename T> __device__ __forceinline__ void mm3(const T* A, const T* B, T* C) {  // C = A B
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+template <typename T> __device__ __forceinline__ void inv3sym(const T* M, T* R) {  // full 3x3 in / out
+    T a = M[0], b = M[1], c = M[2], d = M[4], e = M[5], f = M[8];
+    T A = d * f - e * e, B = c * e - b * f, C = b * e - c * d;
+    T r = T(1) / (a * A + b * B + c * C);
+    R[0] = A * r; R[1] = R[3] = B * r; R[2] = R[6] = C * r;
+    R[4] = (a * f - c * c) * r; R[5] = R[7] = (b * c - a * e) * r; R[8] = (a * d - b * b) * r;
+}
+
+// Build S = P + sigma I + A' R A for this lane's stage, eliminate the inputs, PCR-factorise.
+template <typename T, int NLEV>
+__device__ __forceinline__ void factorize(const Stage<T>& s, Factor<T, NLEV>& f, T sigma, T rd, const T rb[5], int lane,
+                                          int nstage) {
+    const T* a = s.a;
+    T diag[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) diag[i] = s.P[i] + sigma + rb[i] * s.e[i] * s.e[i];
+    T cn[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) cn[i] = shfl_dn(s.c[i], 1);
+    T Dm[9], U[9], Lo[9];
+    Dm[0] = diag[0] + rd * (s.c[0] * s.c[0] + a[0] * a[0] + a[2] * a[2] + a[4] * a[4]);
+    Dm[4] = diag[1] + rd * (s.c[1] * s.c[1] + a[1] * a[1] + a[3] * a[3]);
+    Dm[8] = diag[2] + rd * (s.c[2] * s.c[2] + a[5] * a[5]);
+    Dm[1] = Dm[3] = rd * (a[0] * a[1] + a[2] * a[3]);
+    Dm[2] = Dm[6] = rd * (a[4] * a[5]);
+    Dm[5] = Dm[7] = T(0);
+    T Svv = diag[3] + rd * a[7] * a[7];
+    T Skk = diag[4] + rd * a[6] * a[6];
+    f.sxv0 = rd * a[4] * a[7]; f.sxv2 = rd * a[5] * a[7];
+    f.sxk0 = rd * a[2] * a[6]; f.sxk1 = rd * a[3] * a[6];
+    f.fv = rd * a[7] * cn[2];
+    f.fk = rd * a[6] * cn[1];
+    f.iv = T(1) / Svv;
+    f.ik = T(1) / Skk;
+    // coupling block (row j, col j+1): F_x[i][r] = rd * (coef of x_i in row r of block j+1) * c_{j+1}[r]
+    U[0] = rd * a[0] * cn[0]; U[1] = rd * a[2] * cn[1]; U[2] = rd * a[4] * cn[2];
+    U[3] = rd * a[1] * cn[0]; U[4] = rd * a[3] * cn[1]; U[5] = T(0);
+    U[6] = T(0);              U[7] = T(0);              U[8] = rd * a[5] * cn[2];
+    // Schur complement of the (diagonal) input block
+    {
+        T sxv[3] = {f.sxv0, T(0), f.sxv2}, sxk[3] = {f.sxk0, f.sxk1, T(0)};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) Dm[3 * i + k] -= f.iv * sxv[i] * sxv[k] + f.ik * sxk[i] * sxk[k];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            U[3 * i + 2] -= f.iv * f.fv * sxv[i];
+            U[3 * i + 1] -= f.ik * f.fk * sxk[i];
+        }
+        T add1 = shfl_up(f.ik * f.fk * f.fk, 1), add2 = shfl_up(f.iv * f.fv * f.fv, 1);
+        if (lane > 0) { Dm[4] -= add1; Dm[8] -= add2; }
+    }
+    // Lo = coupling block (row j, col j-1) = U_{j-1}'
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            T v = shfl_up(U[3 * k + i], 1);
+            Lo[3 * i + k] = lane > 0 ? v : T(0);
+        }
+    if (lane >= nstage - 1) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) U[i] = T(0);
+    }
+    if (lane >= nstage) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Lo[i] = T(0);
+    }
+#pragma unroll
+    for (int lev = 0; lev < NLEV; ++lev) {
+        const int sft = 1 << lev;
+        T Di[9];
+        inv3sym(Dm, Di);
+        T Dup[9], Ddn[9], Uup[9], Ldn[9], Lup[9], Udn[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            Dup[i] = shfl_up(Di[i], sft); Ddn[i] = shfl_dn(Di[i], sft);
+            Uup[i] = shfl_up(U[i], sft);  Ldn[i] = shfl_dn(Lo[i], sft);
+            Lup[i] = shfl_up(Lo[i], sft); Udn[i] = shfl_dn(U[i], sft);
+        }
+        const bool has_up = lane >= sft, has_dn = lane + sft < 32;
+        T al[9], be[9];
+        mm3(Lo, Dup, al);
+        mm3(U, Ddn, be);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            if (!has_up) al[i] = T(0);
+            if (!has_dn) be[i] = T(0);
+        }
+        T t1[9], t2[9];
+        mm3(al, Uup, t1);
+        mm3(be, Ldn, t2);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Dm[i] -= t1[i] + t2[i];
+        mm3(al, Lup, t1);
+        mm3(be, Udn, t2);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            Lo[i] = -t1[i]; U[i] = -t2[i];
+            f.al[lev][i] = al[i]; f.be[lev][i] = be[i];
+        }
+    }
+    T Di[9];
+    inv3sym(Dm, Di);
+    f.Dinv[0] = Di[0]; f.Dinv[1] = Di[1]; f.Dinv[2] = Di[2]; f.Dinv[3] = Di[4]; f.Dinv[4] = Di[5]; f.Dinv[5] = Di[8];
+}
+
+// x = S^-1 b
+template <typename T, int NLEV>
+__device__ __forceinline__ void kkt_solve(const Factor<T, NLEV>& f, const T b[5], int lane, T x[5]) {
+    T bv = f.iv * b[3], bk = f.ik * b[4];
+    T bx0 = b[0] - bv * f.sxv0 - bk * f.sxk0;
+    T bx1 = b[1] - bk * f.sxk1;
+    T bx2 = b[2] - bv * f.sxv2;
+    T t1 = shfl_up(bk * f.fk, 1), t2 = shfl_up(bv * f.fv, 1);
+    if (lane > 0) { bx1 -= t1; bx2 -= t2; }
+#pragma unroll
+    for (int lev = 0; lev < NLEV; ++lev) {
+        const int sft = 1 << lev;
+        T u0 = shfl_up(bx0, sft), u1 = shfl_up(bx1, sft), u2 = shfl_up(bx2, sft);
+        T d0 = shfl_dn(bx0, sft), d1 = shfl_dn(bx1, sft), d2 = shfl_dn(bx2, sft);
+        const T* al = f.al[lev];
+        const T* be = f.be[lev];
+        T n0 = bx0 - (al[0] * u0 + al[1] * u1 + al[2] * u2) - (be[0] * d0 + be[1] * d1 + be[2] * d2);
+        T n1 = bx1 - (al[3] * u0 + al[4] * u1 + al[5] * u2) - (be[3] * d0 + be[4] * d1 + be[5] * d2);
+        T n2 = bx2 - (al[6] * u0 + al[7] * u1 + al[8] * u2) - (be[6] * d0 + be[7] * d1 + be[8] * d2);
+        bx0 = n0; bx1 = n1; bx2 = n2;
+    }
+    x[0] = f.Dinv[0] * bx0 + f.Dinv[1] * bx1 + f.Dinv[2] * bx2;
+    x[1] = f.Dinv[1] * bx0 + f.Dinv[3] * bx1 + f.Dinv[4] * bx2;
+    x[2] = f.Dinv[2] * bx0 + f.Dinv[4] * bx1 + f.Dinv[5] * bx2;
+    T xn1 = shfl_dn(x[1], 1), xn2 = shfl_dn(x[2], 1);  // fv, fk are 0 where there is no successor
+    x[3] = f.iv * (b[3] - f.sxv0 * x[0] - f.sxv2 * x[2] - f.fv * xn2);
+    x[4] = f.ik * (b[4] - f.sxk0 * x[0] - f.sxk1 * x[1] - f.fk * xn1);
+}
+
+template <typename T> __device__ __forceinline__ void set_rho(const Stage<T>& s, T rho, T& rd, T rb[5], T rbi[5]) {
+    rd = T(kRhoEqOverIneq) * rho;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        rb[i] = s.ctype[i] < 0 ? T(kRhoMin) : (s.ctype[i] > 0 ? T(kRhoEqOverIneq) * rho : rho);
+        rbi[i] = T(1) / rb[i];
+    }
+}
+
+struct SolveResult {
+    int iters, status;
+};
+
+// The OSQP loop for one scenario (all 32 lanes of the warp call this together).
+// On return w[5] holds the UNSCALED primal stage vector (NaN when OSQP would return no solution).
+template <typename T, int NLEV>
+__device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSettings& st, int lane, int nstage, int nvar,
+                                                  T w[5]) {
+    if (st.scaling > 0) ruiz_scale(s, st.scaling, nvar);
+    else {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { s.D[i] = T(1); s.Eb[i] = T(1); }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s.Ed[i] = T(1);
+        s.cs = T(1);
+    }
+    const T thr = T(kOsqpInfty * kMinScaling);
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+        s.ctype[i] = (s.lo[i] < -thr && s.hi[i] > thr) ? -1 : ((s.hi[i] - s.lo[i] < T(kRhoTol)) ? 1 : 0);
+    T rho = T(st.rho), rd, rb[5], rbi[5];
+    const T sigma = T(st.sigma), alpha = T(st.alpha), oma = T(1) - T(st.alpha);
+    set_rho(s, rho, rd, rb, rbi);
+    Factor<T, NLEV> f;
+    factorize<T, NLEV>(s, f, sigma, rd, rb, lane, nstage);
+    // constant norms
+    T nq_s = T(0), nq_u = T(0);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { nq_s = tmax(nq_s, tabs(s.q[i])); nq_u = tmax(nq_u, tabs(s.q[i] / s.D[i])); }
+    nq_s = warp_max(nq_s); nq_u = warp_max(nq_u);
+    const T cinv = T(1) / s.cs;
+
+    T x[5] = {0, 0, 0, 0, 0}, zd[3] = {0, 0, 0}, zb[5] = {0, 0, 0, 0, 0};
+    T yd[3] = {0, 0, 0}, yb[5] = {0, 0, 0, 0, 0};
+    int status = 0, iter = 0;
+    for (iter = 1; iter <= st.max_iter; ++iter) {
+        T rhs[5], td[3], tb[5], xt[5];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) td[i] = rd * zd[i] - yd[i];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) tb[i] = rb[i] * zb[i] - yb[i];
+        At_apply(s, td, tb, rhs);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) rhs[i] += sigma * x[i] - s.q[i];
+        kkt_solve<T, NLEV>(f, rhs, lane, xt);
+        for (int r = 0; r < st.refine; ++r) {  // iterative refinement: xt += S^-1 (rhs - S xt)
+            T rzd[3], rzb[5], sx[5], res[5], dxr[5];
+            A_apply(s, xt, lane, rzd, rzb);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) rzd[i] *= rd;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) rzb[i] *= rb[i];
+            At_apply(s, rzd, rzb, sx);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) res[i] = rhs[i] - (sx[i] + (s.P[i] + sigma) * xt[i]);
+            kkt_solve<T, NLEV>(f, res, lane, dxr);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) xt[i] += dxr[i];
+        }
+        T ztd[3], ztb[5];
+        A_apply(s, xt, lane, ztd, ztb);
+        T dx[5], dyd[3], dyb[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            T xn = alpha * xt[i] + oma * x[i];
+            dx[i] = xn - x[i];
+            x[i] = xn;
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            T v = alpha * ztd[i] + oma * zd[i];
+            T zn = s.d[i];  // projection onto the equality
+            dyd[i] = rd * (v - zn);
+            yd[i] += dyd[i];
+            zd[i] = zn;
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            T v = alpha * ztb[i] + oma * zb[i];
+            T zn = tmin(tmax(v + rbi[i] * yb[i], s.lo[i]), s.hi[i]);
+            dyb[i] = rb[i] * (v - zn);
+            yb[i] += dyb[i];
+            zb[i] = zn;
+        }
+        const bool can_check = st.check_termination && (iter % st.check_termination == 0);
+        const bool can_adapt = st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0);
+        if (can_check || can_adapt) {
+            T axd[3], axb[5], aty[5];
+            A_apply(s, x, lane, axd, axb);
+            At_apply(s, yd, yb, aty);
+            // scaled and unscaled infinity norms
+            T pr_s = 0, pr_u = 0, nz_s = 0, nz_u = 0, nax_s = 0, nax_u = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                T r = tabs(axd[i] - zd[i]), ei = T(1) / s.Ed[i];
+                pr_s = tmax(pr_s, r); pr_u = tmax(pr_u, r * ei);
+                nz_s = tmax(nz_s, tabs(zd[i])); nz_u = tmax(nz_u, tabs(zd[i]) * ei);
+                nax_s = tmax(nax_s, tabs(axd[i])); nax_u = tmax(nax_u, tabs(axd[i]) * ei);
+            }
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                T r = tabs(axb[i] - zb[i]), ei = T(1) / s.Eb[i];
+                pr_s = tmax(pr_s, r); pr_u = tmax(pr_u, r * ei);
+                nz_s = tmax(nz_s, tabs(zb[i])); nz_u = tmax(nz_u, tabs(zb[i]) * ei);
+                nax_s = tmax(nax_s, tabs(axb[i])); nax_u = tmax(nax_u, tabs(axb[i]) * ei);
+            }
+            T du_s = 0, du_u = 0, npx_s = 0, npx_u = 0, naty_s = 0, naty_u = 0;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                T px = s.P[i] * x[i], di = T(1) / s.D[i];
+                T r = tabs(px + s.q[i] + aty[i]);
+                du_s = tmax(du_s, r); du_u = tmax(du_u, r * di);
+                npx_s = tmax(npx_s, tabs(px)); npx_u = tmax(npx_u, tabs(px) * di);
+                naty_s = tmax(naty_s, tabs(aty[i])); naty_u = tmax(naty_u, tabs(aty[i]) * di);
+            }
+            pr_s = warp_max(pr_s); pr_u = warp_max(pr_u); du_s = warp_max(du_s); du_u = warp_max(du_u) * cinv;
+            nz_s = warp_max(nz_s); nz_u = warp_max(nz_u); nax_s = warp_max(nax_s); nax_u = warp_max(nax_u);
+            npx_s = warp_max(npx_s); npx_u = warp_max(npx_u); naty_s = warp_max(naty_s); naty_u = warp_max(naty_u);
+            if (can_check) {
+                if (pr_u > T(kOsqpInfty) || du_u > T(kOsqpInfty)) { status = -7; break; }
+                const T eps_prim = T(st.eps_abs) + T(st.eps_rel) * tmax(nz_u, nax_u);
+                const T eps_dual = T(st.eps_abs) + T(st.eps_rel) * cinv * tmax(tmax(nq_u, naty_u), npx_u);
+                const bool prim_ok = pr_u < eps_prim, dual_ok = du_u < eps_dual;
+                if (prim_ok && dual_ok) { status = 1; break; }
+                bool pinf = false, dinf = false;
+                if (!prim_ok) {  // is_primal_infeasible
+                    const T epi = T(st.eps_prim_inf);
+                    T pyb[5], ndy = 0, lhs = 0;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        ndy = tmax(ndy, tabs(s.Ed[i] * dyd[i]));
+                        lhs += s.d[i] * dyd[i];  // u*max(dy,0) + l*min(dy,0) with l = u
+                    }
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        T d = dyb[i];
+                        if (s.hi[i] > thr) d = (s.lo[i] < -thr) ? T(0) : tmin(d, T(0));
+                        else if (s.lo[i] < -thr) d = tmax(d, T(0));
+                        pyb[i] = d;
+                        ndy = tmax(ndy, tabs(s.Eb[i] * d));
+                        lhs += s.hi[i] * tmax(d, T(0)) + s.lo[i] * tmin(d, T(0));
+                    }
+                    ndy = warp_max(ndy);
+                    lhs = warp_sum(lhs);
+                    if (ndy > epi && lhs < -epi * ndy) {
+                        T atdy[5], na = 0;
+                        At_apply(s, dyd, pyb, atdy);
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) na = tmax(na, tabs(atdy[i] / s.D[i]));
+                        na = warp_max(na);
+                        pinf = na < epi * ndy;
+                    }
+                }
+                if (!dual_ok && !pinf) {  // is_dual_infeasible
+                    const T edi = T(st.eps_dual_inf);
+                    T ndx = 0, qdx = 0;
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) { ndx = tmax(ndx, tabs(s.D[i] * dx[i])); qdx += s.q[i] * dx[i]; }
+                    ndx = warp_max(ndx);
+                    qdx = warp_sum(qdx);
+                    if (ndx > edi && qdx < -s.cs * edi * ndx) {
+                        T npdx = 0;
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) npdx = tmax(npdx, tabs(s.P[i] * dx[i] / s.D[i]));
+                        npdx = warp_max(npdx);
+                        if (npdx < s.cs * edi * ndx) {
+                            T adxd[3], adxb[5];
+                            A_apply(s, dx, lane, adxd, adxb);
+                            int bad = 0;
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) {
+                                T v = adxd[i] / s.Ed[i];
+                                if (v > edi * ndx || v < -edi * ndx) bad = 1;  // equality rows have finite bounds
+                            }
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) {
+                                T v = adxb[i] / s.Eb[i];
+                                if ((s.hi[i] < thr && v > edi * ndx) || (s.lo[i] > -thr && v < -edi * ndx)) bad = 1;
+                            }
+                            dinf = !__any_sync(kFull, bad);
+                        }
+                    }
+                }
+                if (pinf) { status = -3; break; }
+                if (dinf) { status = -4; break; }
+            }
+            if (can_adapt) {  // adapt_rho / compute_rho_estimate on the scaled residuals
+                T pn = pr_s / (tmax(nz_s, nax_s) + T(1e-10));
+                T dn = du_s / (tmax(tmax(nq_s, naty_s), npx_s) + T(1e-10));
+                T rnew = rho * sqrt(pn / (dn + T(1e-10)));
+                rnew = tmin(tmax(rnew, T(kRhoMin)), T(kRhoMax));
+                if (rnew > rho * T(st.adaptive_rho_tolerance) || rnew < rho / T(st.adaptive_rho_tolerance)) {
+                    rho = rnew;
+                    set_rho(s, rho, rd, rb, rbi);
+                    factorize<T, NLEV>(s, f, sigma, rd, rb, lane, nstage);
+                }
+            }
+        }
+    }
+    if (status == 0) {
+        // max_iter reached: OSQP re-checks with 10x tolerances and may report "solved inaccurate"
+        // etc.; in every such case it RETURNS the iterate, so for the caller only -2 vs NaN matters.
+        status = -2;
+        iter = st.max_iter;
+    }
+    const bool nan_out = (status == -3 || status == -4 || status == -7);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) w[i] = nan_out ? T(NAN) : s.D[i] * x[i];
+    SolveResult r;
+    r.iters = iter;
+    r.status = status;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage loaders
+// ------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ void stage_zero(Stage<T>& s) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s.a[i] = T(0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { s.c[i] = T(0); s.d[i] = T(0); }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { s.e[i] = T(0); s.P[i] = T(0); s.q[i] = T(0); s.lo[i] = T(0); s.hi[i] = T(0); }
+}
+
+__device__ __forceinline__ double clip_inf(double v) { return fmin(fmax(v, -kOsqpInfty), kOsqpInfty); }
+
+// K2-only entry: the QP arrives in the reference's layout (see mpc_b200.h::mpc_solve_qp).
+// Offsets into the fixed CSC pattern: stage k < N occupies 16 values (x columns: 5, 4, 3; then the
+// inputs live at the tail: 2 values per input column); stage N occupies 6.
+template <typename T>
+__device__ __forceinline__ void load_stage_qp(Stage<T>& s, int N, int lane, const double* Pd, const double* q,
+                                              const double* Ax, const double* l, const double* u) {
+    stage_zero(s);
+    if (lane > N) return;
+    const int neq = 3 * (N + 1);
+    const int k = lane;
+    if (k < N) {
+        const double* v = Ax + 12 * k;  // x columns of stage k: [c0 a0 a2 a4 e0 | c1 a1 a3 e1 | c2 a5 e2]
+        s.c[0] = T(v[0]); s.a[0] = T(v[1]); s.a[2] = T(v[2]); s.a[4] = T(v[3]); s.e[0] = T(v[4]);
+        s.c[1] = T(v[5]); s.a[1] = T(v[6]); s.a[3] = T(v[7]); s.e[1] = T(v[8]);
+        s.c[2] = T(v[9]); s.a[5] = T(v[10]); s.e[2] = T(v[11]);
+        const double* w = Ax + 12 * N + 6 + 4 * k;  // input columns: [a7 e3 | a6 e4]
+        s.a[7] = T(w[0]); s.e[3] = T(w[1]); s.a[6] = T(w[2]); s.e[4] = T(w[3]);
+    } else {
+        const double* v = Ax + 12 * N;  // last stage: [c0 e0 | c1 e1 | c2 e2]
+        s.c[0] = T(v[0]); s.e[0] = T(v[1]); s.c[1] = T(v[2]); s.e[1] = T(v[3]); s.c[2] = T(v[4]); s.e[2] = T(v[5]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        s.P[i] = T(Pd[3 * k + i]); s.q[i] = T(q[3 * k + i]);
+        s.d[i] = T(l[3 * k + i]);
+        s.lo[i] = T(clip_inf(l[neq + 3 * k + i])); s.hi[i] = T(clip_inf(u[neq + 3 * k + i]));
+    }
+    if (k < N) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            s.P[3 + i] = T(Pd[neq + 2 * k + i]); s.q[3 + i] = T(q[neq + 2 * k + i]);
+            s.lo[3 + i] = T(clip_inf(l[2 * neq + 2 * k + i])); s.hi[3 + i] = T(clip_inf(u[2 * neq + 2 * k + i]));
+        }
+    }
+}
+
+// K1: MPC._init_problem for stage `lane` (MPC.py:86-155, sbm.py:404-412), fp64 then cast.
+template <typename T>
+__device__ __forceinline__ void assemble_stage(Stage<T>& s, const MpcParams& mp, const PathView& pv, int lane, int wp_id,
+                                               double e_y, double e_psi, const double* cc /*2N*/, const double* ub,
+                                               const double* lb) {
+    stage_zero(s);
+    const int N = mp.N;
+    if (lane > N) return;
+    const int k = lane;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s.c[i] = T(-1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s.e[i] = T(1);
+    if (k < N) {
+        int w0 = wp_id + k;
+        if (w0 >= pv.n_wp) w0 %= pv.n_wp;  // rp.py:364-365 (non-circular end-of-path is flagged by the caller)
+        const double ds = pv.ds_next[w0], kap = pv.kappa[w0], vr = pv.v_ref[w0];
+        s.a[0] = T(1); s.a[1] = T(ds);
+        s.a[2] = T(-(kap * kap) * ds); s.a[3] = T(1); s.a[6] = T(ds);
+        s.a[4] = T(-kap / vr * ds); s.a[5] = T(1); s.a[7] = T(-1 / (vr * vr) * ds);
+        s.e[3] = T(1); s.e[4] = T(1);
+        s.P[0] = T(mp.Q[0]); s.P[1] = T(mp.Q[1]); s.P[2] = T(mp.Q[2]); s.P[3] = T(mp.R[0]); s.P[4] = T(mp.R[1]);
+        s.q[3] = T(-mp.R[0] * vr); s.q[4] = T(-mp.R[1] * kap);
+        // input bounds; speed limit from predicted curvature (MPC.py:86-87,111-113; quirk Q1)
+        const double kp = tan(cc[3 + k] + cc[2 * N - 1]) / mp.L;
+        const double vmax_dyn = sqrt(mp.ay_max / (fabs(kp) + 1e-12));
+        s.lo[3] = T(clip_inf(mp.umin[0])); s.hi[3] = T(clip_inf(fmin(mp.umax[0], vmax_dyn)));
+        s.lo[4] = T(clip_inf(mp.umin[1])); s.hi[4] = T(clip_inf(mp.umax[1]));
+    } else {
+        s.P[0] = T(mp.QN[0]); s.P[1] = T(mp.QN[1]); s.P[2] = T(mp.QN[2]);
+    }
+    if (k == 0) {
+        s.d[0] = T(-e_y); s.d[1] = T(-e_psi); s.d[2] = T(-0.0);  // leq = -x0 (MPC.py:142-143)
+        s.lo[0] = T(e_y); s.hi[0] = T(e_y);                      // MPC.py:119-120 (quirk Q6)
+        s.q[0] = T(-mp.Q[0] * 0.0);
+    } else {
+        int wm = wp_id + k - 1;
+        if (wm >= pv.n_wp) wm %= pv.n_wp;
+        const double ds = pv.ds_next[wm], kap = pv.kappa[wm], vr = pv.v_ref[wm];
+        // uq = B_lin.dot([v_ref, kappa_ref]) - f  (MPC.py:107-108)
+        s.d[0] = T(0);
+        s.d[1] = T(ds * kap);
+        s.d[2] = T((-1 / (vr * vr) * ds) * vr - (1 / vr * ds));
+        const double l_ = lb[k - 1], u_ = ub[k - 1];
+        s.lo[0] = T(clip_inf(l_)); s.hi[0] = T(clip_inf(u_));
+        const double xr = (l_ + u_) / 2;  // MPC.py:125
+        s.q[0] = T(-(k < N ? mp.Q[0] : mp.QN[0]) * xr);
+    }
+    s.lo[1] = T(clip_inf(mp.xmin[1])); s.hi[1] = T(clip_inf(mp.xmax[1]));
+    s.lo[2] = T(clip_inf(mp.xmin[2])); s.hi[2] = T(clip_inf(mp.xmax[2]));
+}
+
+}  // namespace mpcb

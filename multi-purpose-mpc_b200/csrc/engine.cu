@@ -1,0 +1,708 @@
+// engine.cu -- the C ABI of libmpc_b200.so (include/mpc_b200.h): handle, tables, launches, CUDA graph.
+#include "engine.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace mpcb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_OK(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (expr);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(MPC_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));               \
+    } while (0)
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct mpc_engine {
+    mpc_config cfg;
+    MpcParams mp;
+    AdmmSettings st;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    // path
+    int n_wp = 0, circular = 1;
+    double length = 0.0;
+    DevBuf<double> d_wp;      // [13][n_wp]: 12 rows + length_cum
+    DevBuf<double> d_border;  // [n_wp][4]
+    std::vector<double> h_wp, h_border;
+    bool have_path = false, have_border = false;
+    PathView pv{};
+    // grid
+    GridView g{};
+    int words = 0;
+    DevBuf<uint32_t> d_base, d_grids;
+    DevBuf<int> d_obs_px, d_obs_off;
+    int grids_B = 0;  // 0: shared base grid
+    bool have_grid = false;
+    DevBuf<int2> d_rowspan;
+    bool rowspan_valid = false;
+    bool staged = true;
+    DevBuf<int> d_err;
+    // scenarios (engine-owned closed loop)
+    int B = 0;
+    DevBuf<double> s_state, s_spatial, s_control, s_ub, s_lb, s_u, s_acc;
+    DevBuf<int> s_wp_id, s_iters, s_qp_status, s_flags, s_infeas;
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_B = 0;
+    // pinned staging for mpc_step_host
+    double* pin_state = nullptr;
+    double* pin_u = nullptr;
+    int* pin_flags = nullptr;
+    int pin_B = 0;
+    // profiling
+    int profiling = 0;
+    double prof_ms[4] = {0, 0, 0, 0};
+    int64_t prof_launches[4] = {0, 0, 0, 0};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+static void refresh_params(mpc_engine* h) {
+    const mpc_config& c = h->cfg;
+    MpcParams& m = h->mp;
+    m.N = c.N;
+    for (int i = 0; i < 3; ++i) { m.Q[i] = c.Q[i]; m.QN[i] = c.QN[i]; m.xmin[i] = c.xmin[i]; m.xmax[i] = c.xmax[i]; }
+    for (int i = 0; i < 2; ++i) { m.R[i] = c.R[i]; m.umin[i] = c.umin[i]; m.umax[i] = c.umax[i]; }
+    m.ay_max = c.ay_max;
+    m.L = c.car_length;
+    AdmmSettings& s = h->st;
+    s.rho = c.rho; s.sigma = c.sigma; s.alpha = c.alpha; s.eps_abs = c.eps_abs; s.eps_rel = c.eps_rel;
+    s.eps_prim_inf = c.eps_prim_inf; s.eps_dual_inf = c.eps_dual_inf;
+    s.adaptive_rho_tolerance = c.adaptive_rho_tolerance;
+    s.max_iter = c.max_iter; s.scaling = c.scaling; s.check_termination = c.check_termination;
+    s.adaptive_rho_interval = c.adaptive_rho_interval; s.refine = c.refine;
+}
+
+static void drop_graph(mpc_engine* h) {
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+    h->graph_B = 0;
+}
+
+extern "C" {
+
+void mpc_config_default(mpc_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->N = 30;  // simulation.py:100-103
+    c->Q[0] = 1.0; c->R[0] = 0.5; c->QN[0] = 1.0;
+    for (int i = 0; i < 3; ++i) { c->xmin[i] = -INFINITY; c->xmax[i] = INFINITY; }  // simulation.py:110-111
+    c->car_length = 0.12; c->car_width = 0.06; c->Ts = 0.05;                      // simulation.py:53-54
+    const double kmax = std::tan(0.66) / c->car_length;                           // simulation.py:106-109
+    c->umin[0] = 0.0; c->umin[1] = -kmax; c->umax[0] = 1.0; c->umax[1] = kmax;
+    c->ay_max = 4.0;
+    c->rho = 0.1; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-3; c->eps_rel = 1e-3;
+    c->eps_prim_inf = 1e-4; c->eps_dual_inf = 1e-4; c->max_iter = 4000; c->scaling = 10;
+    c->check_termination = 25; c->adaptive_rho_interval = 25; c->adaptive_rho_tolerance = 5.0;
+    c->precision = 0;
+    c->refine = 1;
+}
+
+const char* mpc_last_error(void) { return g_err.c_str(); }
+int mpc_abi_version(void) { return MPC_B200_ABI_VERSION; }
+
+static int validate_cfg(const mpc_config* c) {
+    if (c->N < 3 || c->N > 31) return fail(MPC_E_UNSUPPORTED, "horizon N must be in [3, 31] in this build");
+    if (!(c->car_length > 0) || !(c->Ts > 0)) return fail(MPC_E_INVALID, "car_length and Ts must be positive");
+    if (c->precision != 0 && c->precision != 1) return fail(MPC_E_INVALID, "precision must be 0 (fp32) or 1 (fp64)");
+    if (c->refine < 0 || c->refine > 4) return fail(MPC_E_INVALID, "refine must be in [0, 4]");
+    if (c->max_iter < 1 || c->check_termination < 0 || c->adaptive_rho_interval < 0 || c->scaling < 0)
+        return fail(MPC_E_INVALID, "bad OSQP settings");
+    return 0;
+}
+
+int mpc_engine_create(const mpc_config* cfg, mpc_engine** out) {
+    if (!cfg || !out) return fail(MPC_E_INVALID, "null argument");
+    if (int r = validate_cfg(cfg)) return r;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(MPC_E_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    mpc_engine* h = new mpc_engine();
+    h->cfg = *cfg;
+    refresh_params(h);
+    if (h->d_err.alloc(1) != cudaSuccess) { delete h; return fail(MPC_E_CUDA, "cudaMalloc failed"); }
+    cudaMemset(h->d_err.p, 0, sizeof(int));
+    for (int i = 0; i < 5; ++i) cudaEventCreate(&h->ev[i]);
+    *out = h;
+    return 0;
+}
+
+int mpc_engine_destroy(mpc_engine* h) {
+    if (!h) return 0;
+    cudaStreamSynchronize(h->stream);
+    drop_graph(h);
+    h->d_wp.release(); h->d_border.release(); h->d_base.release(); h->d_grids.release(); h->d_obs_px.release();
+    h->d_obs_off.release(); h->d_rowspan.release(); h->d_err.release();
+    h->s_state.release(); h->s_spatial.release(); h->s_control.release(); h->s_ub.release(); h->s_lb.release();
+    h->s_u.release(); h->s_acc.release(); h->s_wp_id.release(); h->s_iters.release(); h->s_qp_status.release();
+    h->s_flags.release(); h->s_infeas.release();
+    if (h->pin_state) cudaFreeHost(h->pin_state);
+    if (h->pin_u) cudaFreeHost(h->pin_u);
+    if (h->pin_flags) cudaFreeHost(h->pin_flags);
+    for (int i = 0; i < 5; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    delete h;
+    return 0;
+}
+
+int mpc_engine_set_stream(mpc_engine* h, void* s) {
+    if (!h) return fail(MPC_E_INVALID, "null engine");
+    h->stream = (cudaStream_t)s;
+    drop_graph(h);
+    return 0;
+}
+
+int mpc_engine_update_config(mpc_engine* h, const mpc_config* cfg) {
+    if (!h || !cfg) return fail(MPC_E_INVALID, "null argument");
+    if (cfg->N != h->cfg.N) return fail(MPC_E_INVALID, "N cannot change after creation");
+    if (int r = validate_cfg(cfg)) return r;
+    h->cfg = *cfg;
+    refresh_params(h);
+    drop_graph(h);
+    return 0;
+}
+
+int mpc_engine_sync(mpc_engine* h) {
+    if (!h) return fail(MPC_E_INVALID, "null engine");
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+static void bind_path(mpc_engine* h) {
+    const int n = h->n_wp;
+    const double* p = h->d_wp.p;
+    PathView& v = h->pv;
+    v.n_wp = n; v.circular = h->circular;
+    v.x = p; v.y = p + n; v.psi = p + 2 * n; v.kappa = p + 3 * n; v.v_ref = p + 4 * n; v.ds_next = p + 5 * n;
+    v.cos_psi = p + 6 * n; v.sin_psi = p + 7 * n; v.cos_ub = p + 8 * n; v.sin_ub = p + 9 * n; v.cos_lb = p + 10 * n;
+    v.sin_lb = p + 11 * n; v.length_cum = p + 12 * n;
+    v.border = h->d_border.p;
+}
+
+// rows of the grid that the rays of a horizon starting at waypoint w (N waypoints) can touch
+static int compute_rowspan(mpc_engine* h) {
+    h->rowspan_valid = false;
+    if (!h->have_path || !h->have_border || !h->have_grid) return 0;
+    const int n = h->n_wp, N = h->cfg.N;
+    std::vector<int> lo(n), hi(n);
+    for (int k = 0; k < n; ++k) {
+        const double* b = &h->h_border[4 * k];
+        const int y0 = (int)std::floor((b[1] - h->g.oy) / h->g.res), y1 = (int)std::floor((b[3] - h->g.oy) / h->g.res);
+        lo[k] = std::min(y0, y1) - 1;  // anti-aliasing side cells reach one row beyond the main chain
+        hi[k] = std::max(y0, y1) + 1;
+    }
+    std::vector<int2> rs(n);
+    int max_rows = 0;
+    for (int w = 0; w < n; ++w) {
+        int a = 1 << 30, b = -(1 << 30);
+        for (int j = 0; j < N; ++j) {
+            const int k = (w + j) % n;
+            a = std::min(a, lo[k]);
+            b = std::max(b, hi[k]);
+        }
+        a = std::max(a, 0);
+        b = std::min(b, h->g.H - 1);
+        if (b < a) { a = 0; b = 0; }
+        rs[w] = make_int2(a, b);
+        max_rows = std::max(max_rows, b - a + 1);
+    }
+    CUDA_OK(h->d_rowspan.alloc(n));
+    CUDA_OK(cudaMemcpyAsync(h->d_rowspan.p, rs.data(), n * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->rowspan_valid = true;
+    // staging needs the whole grid's worth of shared memory in the worst case
+    h->staged = raycast_smem_bytes(h->g, N, true) <= 200 * 1024;
+    return 0;
+}
+
+int mpc_set_path(mpc_engine* h, const double* h_wp, const double* h_length_cum, const double* h_border, int32_t n_wp,
+                 int32_t circular) {
+    if (!h || !h_wp || !h_length_cum || n_wp < 2) return fail(MPC_E_INVALID, "bad path arguments");
+    h->n_wp = n_wp;
+    h->circular = circular ? 1 : 0;
+    h->h_wp.assign(h_wp, h_wp + 12 * (size_t)n_wp);
+    h->h_wp.insert(h->h_wp.end(), h_length_cum, h_length_cum + n_wp);
+    h->length = h_length_cum[n_wp - 1];
+    CUDA_OK(h->d_wp.alloc(13 * (size_t)n_wp));
+    CUDA_OK(cudaMemcpyAsync(h->d_wp.p, h->h_wp.data(), 13 * (size_t)n_wp * sizeof(double), cudaMemcpyHostToDevice,
+                            h->stream));
+    CUDA_OK(h->d_border.alloc(4 * (size_t)n_wp));
+    h->have_border = false;
+    if (h_border) {
+        h->h_border.assign(h_border, h_border + 4 * (size_t)n_wp);
+        CUDA_OK(cudaMemcpyAsync(h->d_border.p, h_border, 4 * (size_t)n_wp * sizeof(double), cudaMemcpyHostToDevice,
+                                h->stream));
+        h->have_border = true;
+    }
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->have_path = true;
+    bind_path(h);
+    drop_graph(h);
+    return compute_rowspan(h);
+}
+
+int mpc_set_vref(mpc_engine* h, const double* h_vref, int32_t n_wp) {
+    if (!h || !h_vref) return fail(MPC_E_INVALID, "null argument");
+    if (!h->have_path || n_wp != h->n_wp) return fail(MPC_E_STATE, "mpc_set_path first (same n_wp)");
+    memcpy(&h->h_wp[4 * (size_t)n_wp], h_vref, n_wp * sizeof(double));
+    CUDA_OK(cudaMemcpyAsync(h->d_wp.p + 4 * (size_t)n_wp, h_vref, n_wp * sizeof(double), cudaMemcpyHostToDevice,
+                            h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mpc_set_base_grid(mpc_engine* h, const int8_t* data, int32_t H, int32_t W, double ox, double oy, double res) {
+    if (!h || !data || H <= 0 || W <= 0 || !(res > 0)) return fail(MPC_E_INVALID, "bad grid arguments");
+    if (H > 32767 || W > 32767) return fail(MPC_E_UNSUPPORTED, "grid dimensions above 32767 are not supported");
+    GridView& g = h->g;
+    g.H = H; g.W = W; g.ox = ox; g.oy = oy; g.res = res;
+    g.pitch_words = ((W + 511) / 512) * 16;  // 64-byte multiple
+    h->words = H * g.pitch_words;
+    std::vector<uint32_t> bits((size_t)h->words, 0u);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x)
+            if (data[(size_t)y * W + x] == 1) bits[(size_t)y * g.pitch_words + (x >> 5)] |= 1u << (x & 31);
+    CUDA_OK(h->d_base.alloc(h->words));
+    CUDA_OK(cudaMemcpyAsync(h->d_base.p, bits.data(), (size_t)h->words * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->have_grid = true;
+    h->grids_B = 0;
+    drop_graph(h);
+    return compute_rowspan(h);
+}
+
+int mpc_set_obstacles(mpc_engine* h, const double* h_obs, const int32_t* h_off, int32_t B) {
+    if (!h) return fail(MPC_E_INVALID, "null engine");
+    if (!h->have_grid) return fail(MPC_E_STATE, "mpc_set_base_grid first");
+    drop_graph(h);
+    if (B <= 0 || !h_obs || !h_off) { h->grids_B = 0; return 0; }
+    const int n_obs = h_off[B];
+    std::vector<int> px(3 * (size_t)std::max(n_obs, 1));
+    for (int o = 0; o < n_obs; ++o) {
+        const double cx = h_obs[3 * o], cy = h_obs[3 * o + 1], r = h_obs[3 * o + 2];
+        px[3 * o] = (int)std::floor((cx - h->g.ox) / h->g.res);      // map.py:131 via w2m
+        px[3 * o + 1] = (int)std::floor((cy - h->g.oy) / h->g.res);
+        px[3 * o + 2] = (int)std::ceil(r / h->g.res);                // map.py:129
+    }
+    CUDA_OK(h->d_obs_px.alloc(px.size()));
+    CUDA_OK(h->d_obs_off.alloc(B + 1));
+    CUDA_OK(cudaMemcpyAsync(h->d_obs_px.p, px.data(), px.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->d_obs_off.p, h_off, (B + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h->d_grids.alloc((size_t)B * h->words));
+    launch_rasterize(h->d_base.p, h->d_grids.p, h->words, h->g, h->d_obs_px.p, h->d_obs_off.p, B, h->stream);
+    ++h->launches;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->grids_B = B;
+    return 0;
+}
+
+int mpc_get_grid(mpc_engine* h, int32_t b, int8_t* out) {
+    if (!h || !out) return fail(MPC_E_INVALID, "null argument");
+    if (!h->have_grid) return fail(MPC_E_STATE, "no grid");
+    if (h->grids_B && (b < 0 || b >= h->grids_B)) return fail(MPC_E_INVALID, "scenario index out of range");
+    const uint32_t* src = h->grids_B ? h->d_grids.p + (size_t)b * h->words : h->d_base.p;
+    std::vector<uint32_t> bits((size_t)h->words);
+    CUDA_OK(cudaMemcpy(bits.data(), src, (size_t)h->words * 4, cudaMemcpyDeviceToHost));
+    for (int y = 0; y < h->g.H; ++y)
+        for (int x = 0; x < h->g.W; ++x)
+            out[(size_t)y * h->g.W + x] = (bits[(size_t)y * h->g.pitch_words + (x >> 5)] >> (x & 31)) & 1u;
+    return 0;
+}
+
+int mpc_compute_width(mpc_engine* h, double max_width, double* h_ub, double* h_lb, double* h_border) {
+    if (!h) return fail(MPC_E_INVALID, "null engine");
+    if (!h->have_path || !h->have_grid) return fail(MPC_E_STATE, "mpc_set_path and mpc_set_base_grid first");
+    const int n = h->n_wp;
+    DevBuf<double> ub, lb;
+    CUDA_OK(ub.alloc(n));
+    CUDA_OK(lb.alloc(n));
+    CUDA_OK(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), h->stream));
+    launch_compute_width(h->d_base.p, h->g, h->pv, max_width, ub.p, lb.p, h->d_border.p, h->d_err.p, h->stream);
+    ++h->launches;
+    CUDA_OK(cudaGetLastError());
+    h->h_border.resize(4 * (size_t)n);
+    int err = 0;
+    std::vector<double> tu(n), tl(n);
+    CUDA_OK(cudaMemcpyAsync(tu.data(), ub.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaMemcpyAsync(tl.data(), lb.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->h_border.data(), h->d_border.p, 4 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost,
+                            h->stream));
+    CUDA_OK(cudaMemcpyAsync(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    ub.release();
+    lb.release();
+    if (err) return fail(MPC_E_INVALID, "a width ray left the map (the reference raises IndexError, rp.py:279)");
+    if (h_ub) memcpy(h_ub, tu.data(), n * sizeof(double));
+    if (h_lb) memcpy(h_lb, tl.data(), n * sizeof(double));
+    if (h_border) memcpy(h_border, h->h_border.data(), 4 * (size_t)n * sizeof(double));
+    h->have_border = true;
+    drop_graph(h);
+    return compute_rowspan(h);
+}
+
+// ---------------------------------------------------------------------------------------------
+static int need(mpc_engine* h, bool grid, bool border) {
+    if (!h) return fail(MPC_E_INVALID, "null engine");
+    if (!h->have_path) return fail(MPC_E_STATE, "mpc_set_path has not been called");
+    if (grid && !h->have_grid) return fail(MPC_E_STATE, "mpc_set_base_grid has not been called");
+    if (border && !h->have_border) return fail(MPC_E_STATE, "static border cells missing (mpc_compute_width / mpc_set_path)");
+    return 0;
+}
+
+int mpc_localize_t2s(mpc_engine* h, const double* d_state, int32_t* d_wp_id, double* d_spatial, int32_t* d_flags,
+                     int32_t B) {
+    if (int r = need(h, false, false)) return r;
+    if (B <= 0) return 0;
+    launch_localize(d_state, d_wp_id, d_spatial, d_flags, h->pv, h->length, B, h->stream);
+    ++h->launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mpc_update_path_constraints(mpc_engine* h, const int32_t* d_wp_id, int32_t first_offset, int32_t N, double min_width,
+                                double safety_margin, double* d_ub, double* d_lb, double* d_cells_sm, int32_t* d_flags,
+                                int32_t B) {
+    if (int r = need(h, true, true)) return r;
+    if (B <= 0) return 0;
+    if (N < 1 || N > 4096) return fail(MPC_E_INVALID, "bad N");
+    if (h->grids_B && B > h->grids_B) return fail(MPC_E_INVALID, "B exceeds the number of scenario grids");
+    const uint32_t* grids = h->grids_B ? h->d_grids.p : h->d_base.p;
+    const size_t stride = h->grids_B ? (size_t)h->words : 0;
+    // the row-span table is built for the engine's own horizon (first waypoint wp_id+1, N = cfg.N)
+    const bool staged = h->staged && h->rowspan_valid && N == h->cfg.N;
+    if (raycast_smem_bytes(h->g, N, staged) > 200 * 1024) return fail(MPC_E_UNSUPPORTED, "horizon too long for shared memory");
+    launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, d_wp_id, first_offset, N, min_width, safety_margin, d_ub,
+                   d_lb, d_cells_sm, d_flags, B, staged, h->stream);
+    ++h->launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mpc_raycast(mpc_engine* h, const int32_t* d_wp_id, double* d_ub, double* d_lb, double* d_cells_sm, int32_t* d_flags,
+                int32_t B) {
+    if (!h) return fail(MPC_E_INVALID, "null engine");
+    const double sm = h->cfg.car_width / std::sqrt(2.0);  // sbm.py:252
+    return mpc_update_path_constraints(h, d_wp_id, 1, h->cfg.N, 2 * sm, sm, d_ub, d_lb, d_cells_sm, d_flags, B);
+}
+
+int mpc_assemble_solve(mpc_engine* h, const double* d_spatial, const int32_t* d_wp_id, double* d_control,
+                       const double* d_ub, const double* d_lb, int32_t* d_infeas, double* d_u_out, double* d_x_out,
+                       int32_t* d_iters, int32_t* d_qp_status, int32_t* d_flags, int32_t B) {
+    if (int r = need(h, false, false)) return r;
+    if (B <= 0) return 0;
+    if (!d_spatial || !d_wp_id || !d_control || !d_ub || !d_lb || !d_infeas || !d_u_out)
+        return fail(MPC_E_INVALID, "null device pointer");
+    int r = launch_assemble_solve(h->cfg.precision, h->mp, h->st, h->pv, d_spatial, d_wp_id, d_control, d_ub, d_lb,
+                                  d_infeas, d_u_out, d_x_out, d_iters, d_qp_status, d_flags, B, h->stream);
+    if (r) return fail(r, "unsupported horizon");
+    ++h->launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mpc_solve_qp(mpc_engine* h, const double* d_Pd, const double* d_q, const double* d_Ax, const double* d_l,
+                 const double* d_u, double* d_x_out, int32_t* d_iters, int32_t* d_qp_status, int32_t B) {
+    if (!h) return fail(MPC_E_INVALID, "null engine");
+    if (B <= 0) return 0;
+    if (!d_Pd || !d_q || !d_Ax || !d_l || !d_u) return fail(MPC_E_INVALID, "null device pointer");
+    int r = launch_solve_qp(h->cfg.precision, h->cfg.N, h->st, d_Pd, d_q, d_Ax, d_l, d_u, d_x_out, d_iters, d_qp_status,
+                            B, h->stream);
+    if (r) return fail(r, "unsupported horizon");
+    ++h->launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mpc_rollout(mpc_engine* h, double* d_state, const double* d_spatial, const int32_t* d_wp_id, const double* d_u,
+                const int32_t* d_flags, int32_t B) {
+    if (int r = need(h, false, false)) return r;
+    if (B <= 0) return 0;
+    launch_rollout(d_state, d_spatial, d_wp_id, d_u, d_flags, h->pv, h->cfg.car_length, h->cfg.Ts, B, h->stream);
+    ++h->launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// engine-owned scenarios
+// ---------------------------------------------------------------------------------------------
+int mpc_scenarios_init(mpc_engine* h, const double* h_state, int32_t B) {
+    if (int r = need(h, true, true)) return r;
+    if (B <= 0 || !h_state) return fail(MPC_E_INVALID, "bad scenario arguments");
+    if (h->grids_B && B > h->grids_B) return fail(MPC_E_INVALID, "B exceeds the number of scenario grids");
+    const int N = h->cfg.N;
+    CUDA_OK(h->s_state.alloc(4 * (size_t)B));
+    CUDA_OK(h->s_spatial.alloc(2 * (size_t)B));
+    CUDA_OK(h->s_control.alloc(2 * (size_t)N * B));
+    CUDA_OK(h->s_ub.alloc((size_t)N * B));
+    CUDA_OK(h->s_lb.alloc((size_t)N * B));
+    CUDA_OK(h->s_u.alloc(2 * (size_t)B));
+    CUDA_OK(h->s_acc.alloc(5 * (size_t)B));
+    CUDA_OK(h->s_wp_id.alloc(B));
+    CUDA_OK(h->s_iters.alloc(B));
+    CUDA_OK(h->s_qp_status.alloc(B));
+    CUDA_OK(h->s_flags.alloc(B));
+    CUDA_OK(h->s_infeas.alloc(B));
+    h->B = B;
+    drop_graph(h);
+    return mpc_scenarios_set_state(h, h_state, nullptr, nullptr);
+}
+
+int mpc_scenarios_set_state(mpc_engine* h, const double* h_state, const double* h_control, const int32_t* h_infeas) {
+    if (!h || h->B <= 0) return fail(MPC_E_STATE, "mpc_scenarios_init first");
+    const int B = h->B, N = h->cfg.N;
+    cudaStream_t s = h->stream;
+    if (h_state) CUDA_OK(cudaMemcpyAsync(h->s_state.p, h_state, 4 * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (h_control)
+        CUDA_OK(cudaMemcpyAsync(h->s_control.p, h_control, 2 * (size_t)N * B * sizeof(double), cudaMemcpyHostToDevice, s));
+    else
+        CUDA_OK(cudaMemsetAsync(h->s_control.p, 0, 2 * (size_t)N * B * sizeof(double), s));  // MPC.py:56
+    if (h_infeas) CUDA_OK(cudaMemcpyAsync(h->s_infeas.p, h_infeas, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, s));
+    else CUDA_OK(cudaMemsetAsync(h->s_infeas.p, 0, (size_t)B * sizeof(int), s));             // MPC.py:53
+    CUDA_OK(cudaMemsetAsync(h->s_flags.p, 0, (size_t)B * sizeof(int), s));
+    CUDA_OK(cudaMemsetAsync(h->s_iters.p, 0, (size_t)B * sizeof(int), s));
+    CUDA_OK(cudaMemsetAsync(h->s_qp_status.p, 0, (size_t)B * sizeof(int), s));
+    CUDA_OK(cudaMemsetAsync(h->s_acc.p, 0, 5 * (size_t)B * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(h->s_wp_id.p, 0, (size_t)B * sizeof(int), s));
+    CUDA_OK(cudaMemsetAsync(h->s_spatial.p, 0, 2 * (size_t)B * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(h->s_u.p, 0, 2 * (size_t)B * sizeof(double), s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// the four kernels of one closed-loop step (simulation.py:137-140), optionally bracketed by events
+static int enqueue_step(mpc_engine* h, bool with_stats, bool timed) {
+    const int B = h->B;
+    cudaStream_t s = h->stream;
+    if (timed) cudaEventRecord(h->ev[0], s);
+    launch_localize(h->s_state.p, h->s_wp_id.p, h->s_spatial.p, h->s_flags.p, h->pv, h->length, B, s);
+    if (timed) cudaEventRecord(h->ev[1], s);
+    const double sm = h->cfg.car_width / std::sqrt(2.0);
+    const uint32_t* grids = h->grids_B ? h->d_grids.p : h->d_base.p;
+    const size_t stride = h->grids_B ? (size_t)h->words : 0;
+    launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm, h->s_ub.p,
+                   h->s_lb.p, nullptr, h->s_flags.p, B, h->staged && h->rowspan_valid, s);
+    if (timed) cudaEventRecord(h->ev[2], s);
+    int r = launch_assemble_solve(h->cfg.precision, h->mp, h->st, h->pv, h->s_spatial.p, h->s_wp_id.p, h->s_control.p,
+                                  h->s_ub.p, h->s_lb.p, h->s_infeas.p, h->s_u.p, nullptr, h->s_iters.p,
+                                  h->s_qp_status.p, h->s_flags.p, B, s);
+    if (r) return fail(r, "unsupported horizon");
+    if (timed) cudaEventRecord(h->ev[3], s);
+    if (with_stats) launch_accumulate_stats(h->s_flags.p, h->s_iters.p, h->s_spatial.p, h->s_acc.p, B, s);
+    launch_rollout(h->s_state.p, h->s_spatial.p, h->s_wp_id.p, h->s_u.p, h->s_flags.p, h->pv, h->cfg.car_length,
+                   h->cfg.Ts, B, s);
+    if (timed) cudaEventRecord(h->ev[4], s);
+    h->launches += with_stats ? 5 : 4;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mpc_step(mpc_engine* h) {
+    if (!h || h->B <= 0) return fail(MPC_E_STATE, "mpc_scenarios_init first");
+    if (int r = need(h, true, true)) return r;
+    return enqueue_step(h, false, false);
+}
+
+static int ensure_graph(mpc_engine* h) {
+    if (h->graph_exec && h->graph_B == h->B) return 0;
+    drop_graph(h);
+    cudaStream_t cap = h->stream;
+    cudaStream_t own = nullptr;
+    if (cap == nullptr) {  // the legacy default stream cannot be captured
+        CUDA_OK(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+        cap = own;
+    }
+    cudaStream_t saved = h->stream;
+    h->stream = cap;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    int r = 0;
+    if (e == cudaSuccess) {
+        const int64_t l0 = h->launches;
+        r = enqueue_step(h, true, false);
+        h->launches = l0;
+        e = cudaStreamEndCapture(cap, &graph);
+    }
+    h->stream = saved;
+    if (own) cudaStreamDestroy(own);
+    if (e != cudaSuccess || r) {
+        if (graph) cudaGraphDestroy(graph);
+        return r ? r : fail(MPC_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    }
+    e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(MPC_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+    h->graph_B = h->B;
+    return 0;
+}
+
+__global__ void reduce_stats_kernel(const double* __restrict__ acc, const int* __restrict__ flags, int B,
+                                    double* __restrict__ out8) {
+    __shared__ double sh[8][256];
+    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        v[0] += acc[b];
+        v[1] += acc[b];
+        v[2] += acc[(size_t)B + b];
+        v[3] += acc[2 * (size_t)B + b];
+        v[4] += (flags[b] & MPC_ST_DEAD) ? 1.0 : 0.0;
+        v[5] += (flags[b] & MPC_ST_FINISHED) ? 1.0 : 0.0;
+        v[6] += acc[3 * (size_t)B + b];
+        v[7] = fmax(v[7], acc[4 * (size_t)B + b]);
+    }
+    for (int i = 0; i < 8; ++i) sh[i][threadIdx.x] = v[i];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int i = 0; i < 8; ++i)
+                sh[i][threadIdx.x] = i == 7 ? fmax(sh[i][threadIdx.x], sh[i][threadIdx.x + s])
+                                            : sh[i][threadIdx.x] + sh[i][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x < 8) out8[threadIdx.x] = sh[threadIdx.x][0];
+}
+
+int mpc_run_closed_loop(mpc_engine* h, int32_t max_steps, double* h_stats) {
+    if (!h || h->B <= 0) return fail(MPC_E_STATE, "mpc_scenarios_init first");
+    if (int r = need(h, true, true)) return r;
+    if (max_steps < 0) return fail(MPC_E_INVALID, "max_steps < 0");
+    if (h->profiling) {
+        for (int k = 0; k < max_steps; ++k) {
+            if (int r = enqueue_step(h, true, true)) return r;
+            CUDA_OK(cudaEventSynchronize(h->ev[4]));
+            for (int i = 0; i < 4; ++i) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
+                h->prof_ms[i] += ms;
+                h->prof_launches[i] += 1;
+            }
+        }
+    } else {
+        if (int r = ensure_graph(h)) return r;
+        for (int k = 0; k < max_steps; ++k) CUDA_OK(cudaGraphLaunch(h->graph_exec, h->stream));
+        h->launches += 5 * (int64_t)max_steps;
+    }
+    if (h_stats) {
+        DevBuf<double> out;
+        CUDA_OK(out.alloc(8));
+        reduce_stats_kernel<<<1, 256, 0, h->stream>>>(h->s_acc.p, h->s_flags.p, h->B, out.p);
+        ++h->launches;
+        CUDA_OK(cudaMemcpyAsync(h_stats, out.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_OK(cudaStreamSynchronize(h->stream));
+        out.release();
+    } else {
+        CUDA_OK(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int mpc_step_host(mpc_engine* h, double* h_state, double* h_u_out, int32_t* h_flags) {
+    if (!h || h->B <= 0) return fail(MPC_E_STATE, "mpc_scenarios_init first");
+    if (int r = need(h, true, true)) return r;
+    if (!h_state || !h_u_out) return fail(MPC_E_INVALID, "null host pointer");
+    const int B = h->B;
+    if (h->pin_B < B) {
+        if (h->pin_state) cudaFreeHost(h->pin_state);
+        if (h->pin_u) cudaFreeHost(h->pin_u);
+        if (h->pin_flags) cudaFreeHost(h->pin_flags);
+        CUDA_OK(cudaMallocHost(&h->pin_state, 4 * (size_t)B * sizeof(double)));
+        CUDA_OK(cudaMallocHost(&h->pin_u, 2 * (size_t)B * sizeof(double)));
+        CUDA_OK(cudaMallocHost(&h->pin_flags, (size_t)B * sizeof(int)));
+        h->pin_B = B;
+    }
+    cudaStream_t s = h->stream;
+    memcpy(h->pin_state, h_state, 4 * (size_t)B * sizeof(double));
+    CUDA_OK(cudaMemcpyAsync(h->s_state.p, h->pin_state, 4 * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (int r = enqueue_step(h, false, false)) return r;
+    CUDA_OK(cudaMemcpyAsync(h->pin_state, h->s_state.p, 4 * (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(h->pin_u, h->s_u.p, 2 * (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(h->pin_flags, h->s_flags.p, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    memcpy(h_state, h->pin_state, 4 * (size_t)B * sizeof(double));
+    memcpy(h_u_out, h->pin_u, 2 * (size_t)B * sizeof(double));
+    if (h_flags) memcpy(h_flags, h->pin_flags, (size_t)B * sizeof(int));
+    return 0;
+}
+
+int mpc_scenarios_ptrs(mpc_engine* h, double** d_state, double** d_spatial, int32_t** d_wp_id, double** d_control,
+                       double** d_ub, double** d_lb, double** d_u, int32_t** d_iters, int32_t** d_qp_status,
+                       int32_t** d_flags, int32_t** d_infeas) {
+    if (!h || h->B <= 0) return fail(MPC_E_STATE, "mpc_scenarios_init first");
+    if (d_state) *d_state = h->s_state.p;
+    if (d_spatial) *d_spatial = h->s_spatial.p;
+    if (d_wp_id) *d_wp_id = h->s_wp_id.p;
+    if (d_control) *d_control = h->s_control.p;
+    if (d_ub) *d_ub = h->s_ub.p;
+    if (d_lb) *d_lb = h->s_lb.p;
+    if (d_u) *d_u = h->s_u.p;
+    if (d_iters) *d_iters = h->s_iters.p;
+    if (d_qp_status) *d_qp_status = h->s_qp_status.p;
+    if (d_flags) *d_flags = h->s_flags.p;
+    if (d_infeas) *d_infeas = h->s_infeas.p;
+    return 0;
+}
+
+int mpc_scenarios_read(mpc_engine* h, double* h_state, double* h_control, double* h_u, int32_t* h_iters,
+                       int32_t* h_qp_status, int32_t* h_flags, int32_t* h_infeas, int32_t* h_wp_id, double* h_ub,
+                       double* h_lb) {
+    if (!h || h->B <= 0) return fail(MPC_E_STATE, "mpc_scenarios_init first");
+    const size_t B = h->B, N = h->cfg.N;
+    cudaStream_t s = h->stream;
+    CUDA_OK(cudaStreamSynchronize(s));
+    if (h_state) CUDA_OK(cudaMemcpy(h_state, h->s_state.p, 4 * B * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_control) CUDA_OK(cudaMemcpy(h_control, h->s_control.p, 2 * N * B * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_u) CUDA_OK(cudaMemcpy(h_u, h->s_u.p, 2 * B * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_iters) CUDA_OK(cudaMemcpy(h_iters, h->s_iters.p, B * sizeof(int), cudaMemcpyDeviceToHost));
+    if (h_qp_status) CUDA_OK(cudaMemcpy(h_qp_status, h->s_qp_status.p, B * sizeof(int), cudaMemcpyDeviceToHost));
+    if (h_flags) CUDA_OK(cudaMemcpy(h_flags, h->s_flags.p, B * sizeof(int), cudaMemcpyDeviceToHost));
+    if (h_infeas) CUDA_OK(cudaMemcpy(h_infeas, h->s_infeas.p, B * sizeof(int), cudaMemcpyDeviceToHost));
+    if (h_wp_id) CUDA_OK(cudaMemcpy(h_wp_id, h->s_wp_id.p, B * sizeof(int), cudaMemcpyDeviceToHost));
+    if (h_ub) CUDA_OK(cudaMemcpy(h_ub, h->s_ub.p, N * B * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_lb) CUDA_OK(cudaMemcpy(h_lb, h->s_lb.p, N * B * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int64_t mpc_launch_count(mpc_engine* h) { return h ? h->launches : 0; }
+
+int mpc_set_profiling(mpc_engine* h, int32_t on) {
+    if (!h) return fail(MPC_E_INVALID, "null engine");
+    h->profiling = on ? 1 : 0;
+    for (int i = 0; i < 4; ++i) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
+    return 0;
+}
+
+int mpc_get_profile(mpc_engine* h, double* h_ms, int64_t* h_launches) {
+    if (!h) return fail(MPC_E_INVALID, "null engine");
+    for (int i = 0; i < 4; ++i) {
+        if (h_ms) h_ms[i] = h->prof_ms[i];
+        if (h_launches) h_launches[i] = h->prof_launches[i];
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,40 @@
+// engine.h -- internal declarations shared by the translation units of libmpc_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/mpc_b200.h"
+#include "admm.cuh"
+
+namespace mpcb {
+
+struct GridView {
+    int H, W, pitch_words;  // row pitch in 32-bit words (multiple of 16 -> 64 B)
+    double ox, oy, res;
+};
+
+// geometry.cu
+void launch_rasterize(const uint32_t* base, uint32_t* grids, int words, const GridView& g, const int* obs_px,
+                      const int* offsets, int B, cudaStream_t st);
+void launch_compute_width(const uint32_t* grid, const GridView& g, const PathView& pv, double max_width, double* ub,
+                          double* lb, double* border, int* err, cudaStream_t st);
+size_t raycast_smem_bytes(const GridView& g, int N, bool staged);
+void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridView& g, const PathView& pv,
+                    const int2* rowspan, const int* wp_id, int first_offset, int N, double min_width, double sm,
+                    double* ub, double* lb, double* cells_sm, int* flags, int B, bool staged, cudaStream_t st);
+void launch_localize(const double* state, int* wp_id, double* spatial, int* flags, const PathView& pv, double length,
+                     int B, cudaStream_t st);
+void launch_rollout(double* state, const double* spatial, const int* wp_id, const double* u, const int* flags,
+                    const PathView& pv, double L, double Ts, int B, cudaStream_t st);
+void launch_accumulate_stats(const int* flags, const int* iters, const double* spatial, double* acc, int B,
+                             cudaStream_t st);
+
+// admm.cu
+int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax,
+                    const double* l, const double* u, double* x_out, int* iters, int* status, int B, cudaStream_t s);
+int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings& st, const PathView& pv,
+                          const double* spatial, const int* wp_id, double* control, const double* ub, const double* lb,
+                          int* infeas, double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
+                          cudaStream_t s);
+
+}  // namespace mpcb

@@ -1,0 +1,465 @@
+// geometry.cu -- K3 (dynamic raycast), K3b (static width), obstacle rasteriser, K4 (localise + t2s,
+// rollout) for sm_100a.  Compiled with -fmad=false: every fp64 expression here must round exactly
+// like the reference's numpy / CPython arithmetic (no FMA contraction), because grid cells and
+// drivable widths are compared bit-for-bit.
+//
+// Reference: src/reference_path.py:206-287 (static width), 466-648 (update_path_constraints),
+// src/map.py:77-137 (w2m, m2w, add_obstacles), src/spatial_bicycle_models.py:183-279 (t2s, drive,
+// get_current_waypoint); skimage.draw.line_aa cell order restated from skimage/draw/_draw.pyx.
+#include "engine.h"
+
+namespace mpcb {
+
+__device__ __forceinline__ double np_mod(double a, double b) {  // numpy floor-mod, b > 0
+    double m = fmod(a, b);
+    if (m != 0.0) { if (m < 0) m += b; } else m = 0.0;
+    return m;
+}
+__device__ __forceinline__ double sq(double x) { return x * x; }
+
+__device__ __forceinline__ void w2m(const GridView& g, double x, double y, int& dx, int& dy) {
+    dx = (int)floor((x - g.ox) / g.res);  // map.py:85  (IEEE divide, not reciprocal-multiply)
+    dy = (int)floor((y - g.oy) / g.res);  // map.py:86
+}
+__device__ __forceinline__ void m2w(const GridView& g, int dx, int dy, double& x, double& y) {
+    x = ((double)dx + 0.5) * g.res + g.ox;  // map.py:98
+    y = ((double)dy + 0.5) * g.res + g.oy;  // map.py:99
+}
+
+// skimage.draw.line_aa(r0, c0, r1, c1) cell sequence; the reference passes (x, y) as (r, c).
+// Usage:  LineAA it(x0,y0,x1,y1); do { visit(it.x, it.y) for each emitted cell } -- see walk().
+template <typename Visit> __device__ __forceinline__ void line_aa_walk(int r0, int c0, int r1, int c1, Visit&& visit) {
+    const int dc = abs(c0 - c1), dr = abs(r0 - r1);
+    float err = (float)(dc - dr);
+    const int sign_c = (c0 < c1) ? 1 : -1, sign_r = (r0 < r1) ? 1 : -1;
+    const float ed = (dc + dr == 0) ? 1.0f : (float)sqrt((double)(dc * dc + dr * dr));
+    int c = c0, r = r0;
+    for (;;) {
+        if (!visit(r, c)) return;
+        const float err_prime = err;
+        const int c_prime = c;
+        if (2 * err_prime >= -dc) {
+            if (c == c1) break;
+            if (err_prime + dr < ed) { if (!visit(r + sign_r, c)) return; }
+            err -= dr;
+            c += sign_c;
+        }
+        if (2 * err_prime <= dr) {
+            if (r == r1) break;
+            if (dc - err_prime < ed) { if (!visit(r, c_prime + sign_c)) return; }
+            err += dc;
+            r += sign_r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// obstacle rasteriser: Map.add_obstacles (map.py:126-137) into per-scenario bit-packed grids
+// ------------------------------------------------------------------------------------------------
+// one CTA per scenario; grid words staged in shared memory, discs applied with atomicAnd.
+__global__ void rasterize_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ grids, int words, GridView g,
+                                 const int* __restrict__ obs_px /*[n][3] cx,cy,r*/, const int* __restrict__ offsets) {
+    extern __shared__ uint32_t sm[];
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) sm[i] = base[i];
+    __syncthreads();
+    for (int o = offsets[b]; o < offsets[b + 1]; ++o) {
+        const int cx = obs_px[3 * o], cy = obs_px[3 * o + 1], r = obs_px[3 * o + 2];
+        const int side = 2 * r;  // window [-r, r) (np.ogrid[-r:r], quirk Q5)
+        for (int t = threadIdx.x; t < side * side; t += blockDim.x) {
+            const int dy = t / side - r, dx = t % side - r;
+            if (dx * dx + dy * dy <= r * r) {
+                const int x = cx + dx, y = cy + dy;
+                if (x >= 0 && y >= 0 && x < g.W && y < g.H) atomicAnd(&sm[y * g.pitch_words + (x >> 5)], ~(1u << (x & 31)));
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t* out = grids + (size_t)b * words;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) out[i] = sm[i];
+}
+
+void launch_rasterize(const uint32_t* base, uint32_t* grids, int words, const GridView& g, const int* obs_px,
+                      const int* offsets, int B, cudaStream_t st) {
+    cudaFuncSetAttribute(rasterize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, words * 4);
+    rasterize_kernel<<<B, 256, words * 4, st>>>(base, grids, words, g, obs_px, offsets);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3b: ReferencePath._compute_width / _get_min_width (rp.py:206-287)
+// one warp per (waypoint, side); lanes 0..8 walk the 9 anti-aliased rays (target cell +-1).
+// ------------------------------------------------------------------------------------------------
+__global__ void compute_width_kernel(const uint32_t* __restrict__ grid, GridView g, PathView pv, double max_width,
+                                     double* __restrict__ out_ub, double* __restrict__ out_lb,
+                                     double* __restrict__ out_border, int* __restrict__ err_flag) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= 2 * pv.n_wp) return;
+    const int k = warp >> 1, side = warp & 1;
+    const double wx = pv.x[k], wy = pv.y[k];
+    const double ca = side == 0 ? pv.cos_ub[k] : pv.cos_lb[k];  // angle = mod(psi +- pi/2 + pi, 2pi) - pi (rp.py:221-225)
+    const double sa = side == 0 ? pv.sin_ub[k] : pv.sin_lb[k];
+    int tx, ty, px, py;
+    w2m(g, wx + max_width * ca, wy + max_width * sa, tx, ty);  // rp.py:227
+    w2m(g, wx, wy, px, py);                                    // rp.py:263
+    double best = max_width;
+    int bx = 0, by = 0, found = 0, bad = 0;
+    if (lane < 9) {
+        const int i = lane / 3 - 1, j = lane % 3 - 1;  // tn_x = t_x + i (outer), tn_y = t_y + j (inner), rp.py:257-260
+        line_aa_walk(px, py, tx + i, ty + j, [&](int x, int y) {
+            int xx = x < 0 ? x + g.W : x, yy = y < 0 ? y + g.H : y;  // numpy negative index wrap
+            if (xx < 0 || yy < 0 || xx >= g.W || yy >= g.H) { bad = 1; return false; }
+            const uint32_t wd = grid[yy * g.pitch_words + (xx >> 5)];
+            if (!((wd >> (xx & 31)) & 1u)) {  // occupied (rp.py:279)
+                double cx, cy;
+                m2w(g, x, y, cx, cy);
+                const double d = sqrt(sq(wx - cx) + sq(wy - cy));  // rp.py:282
+                if (d < best) { best = d; bx = x; by = y; found = 1; }
+            }
+            return true;
+        });
+    }
+    if (__any_sync(0xffffffffu, bad)) { if (lane == 0) atomicOr(err_flag, MPC_ST_INDEX_ERROR); }
+    // sequential `<` over paths in order: the smallest distance wins, ties go to the earliest path
+    double wbest = best;
+    int wl = found ? lane : 64;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, wbest, s);
+        const int ol = __shfl_xor_sync(0xffffffffu, wl, s);
+        if (ob < wbest || (ob == wbest && ol < wl)) { wbest = ob; wl = ol; }
+    }
+    const int src = wl < 32 ? wl : 0;
+    bx = __shfl_sync(0xffffffffu, bx, src);
+    by = __shfl_sync(0xffffffffu, by, src);
+    if (lane == 0) {
+        double cx, cy;
+        if (wl < 32) m2w(g, bx, by, cx, cy);
+        else m2w(g, tx + 1, ty + 1, cx, cy);  // rp.py:274 with the loop-leaked (t_x+1, t_y+1) (quirk Q3)
+        if (side == 0) out_ub[k] = wbest; else out_lb[k] = -1 * wbest;  // rp.py:236-237
+        out_border[4 * k + 2 * side] = cx;
+        out_border[4 * k + 2 * side + 1] = cy;
+    }
+}
+
+void launch_compute_width(const uint32_t* grid, const GridView& g, const PathView& pv, double max_width, double* ub,
+                          double* lb, double* border, int* err, cudaStream_t st) {
+    const int warps = 2 * pv.n_wp;
+    compute_width_kernel<<<(warps * 32 + 127) / 128, 128, 0, st>>>(grid, g, pv, max_width, ub, lb, border, err);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: ReferencePath.update_path_constraints (rp.py:522-648) on per-scenario bit-packed grids.
+// One warp per scenario.  The rows of the grid that the horizon's rays can touch are one
+// contiguous byte range (full 64 B-pitch rows): a single cp.async.bulk (TMA bulk copy, UBLKCP)
+// stages it in shared memory, signalled through an mbarrier.  Phase 1: lane n walks the ray of
+// horizon waypoint n (rp.py:466-520) and records its free segments; phase 2: every waypoint with
+// <= 1 candidate (or n == 0) is finalised independently; phase 3: the few waypoints with >= 2
+// candidates are resolved in order (nearest to the projected previous pick, rp.py:552-586).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxSeg = 8;
+
+struct RayOut {
+    double ub, lb, cells_sm[4], cells[4];
+};
+
+__device__ __forceinline__ RayOut finalize_wp(const PathView& pv, int k, double ubx, double uby, double lbx, double lby,
+                                              double sm) {
+    RayOut o;
+    const double wx = pv.x[k], wy = pv.y[k], psi = pv.psi[k];
+    const double PI = 3.141592653589793;
+    const double angle_ub = np_mod(atan2(uby - wy, ubx - wx) - psi + PI, 2 * PI) - PI;  // rp.py:598
+    const double angle_lb = np_mod(atan2(lby - wy, lbx - wx) - psi + PI, 2 * PI) - PI;  // rp.py:600
+    const double sgu = (double)((angle_ub > 0) - (angle_ub < 0)), sgl = (double)((angle_lb > 0) - (angle_lb < 0));
+    double ub = sgu * sqrt(sq(ubx - wx) + sq(uby - wy));  // rp.py:606
+    double lb = sgl * sqrt(sq(lbx - wx) + sq(lby - wy));  // rp.py:608
+    ub -= sm;
+    lb += sm;
+    if (ub < lb) { ub = 0.0; lb = 0.0; }  // rp.py:616-619
+    const double cu = pv.cos_ub[k], su = pv.sin_ub[k], cl = pv.cos_lb[k], sl = pv.sin_lb[k];
+    o.cells_sm[0] = wx + ub * cu; o.cells_sm[1] = wy + ub * su;  // rp.py:627
+    o.cells_sm[2] = wx - lb * cl; o.cells_sm[3] = wy - lb * sl;  // rp.py:629
+    o.cells[0] = wx + (ub + sm) * cu; o.cells[1] = wy + (ub + sm) * su;  // rp.py:633
+    o.cells[2] = wx - (lb - sm) * cl; o.cells[3] = wy - (lb - sm) * sl;  // rp.py:635
+    o.ub = ub;
+    o.lb = lb;
+    return o;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool STAGED>
+__global__ void __launch_bounds__(32)
+raycast_kernel(const uint32_t* __restrict__ grids, size_t grid_stride_words, GridView g, PathView pv,
+               const int2* __restrict__ rowspan /*[n_wp]: rows touched by a horizon starting at wp*/,
+               const int* __restrict__ wp_id, int first_offset, int N, double min_width, double sm,
+               double* __restrict__ ub_out, double* __restrict__ lb_out, double* __restrict__ cells_sm_out,
+               int* __restrict__ flags, int B) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (b >= B) return;
+    const int fl = flags ? flags[b] : 0;
+    if (fl & (MPC_ST_DEAD | MPC_ST_FINISHED)) return;
+    // shared layout: [grid rows][segments: N * kMaxSeg * int4][nseg: N ints][cells: N*4 doubles][mbar]
+    uint32_t* srow = reinterpret_cast<uint32_t*>(smem_raw);
+    const int max_rows_words = STAGED ? g.H * g.pitch_words : 0;
+    short4* segs = reinterpret_cast<short4*>(smem_raw + (size_t)max_rows_words * 4);
+    double* prev_cells = reinterpret_cast<double*>(segs + (size_t)N * kMaxSeg);
+    int* nsegs = reinterpret_cast<int*>(prev_cells + (size_t)N * 4);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(nsegs + ((N + 1) & ~1));
+
+    long first = (long)wp_id[b] + first_offset;
+    int status = 0;
+    if (!pv.circular && first + N - 1 >= pv.n_wp) status |= MPC_ST_END_OF_PATH;  // rp.py:367-369
+    const int first_w = (int)(first % pv.n_wp);
+    const uint32_t* gsrc = grids + (size_t)b * grid_stride_words;
+    int row0 = 0;
+    if (STAGED) {
+        const int2 rs = rowspan[first_w];
+        row0 = rs.x;
+        const uint32_t bytes = (uint32_t)(rs.y - rs.x + 1) * g.pitch_words * 4;
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(srow)),
+                "l"(gsrc + (size_t)row0 * g.pitch_words), "r"(bytes), "r"(smem_u32(mbar))
+                : "memory");
+        }
+        __syncwarp();
+        // wait for the bulk copy (phase 0)
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(smem_u32(mbar))
+                : "memory");
+        }
+    }
+    // ---- phase 1: free segments per horizon waypoint (rp.py:466-520) ----
+    for (int n = lane; n < N; n += 32) {
+        const int k = (first_w + n) % pv.n_wp;
+        const double* bc = pv.border + 4 * k;
+        int ubx, uby, lbx, lby;
+        w2m(g, bc[0], bc[1], ubx, uby);  // rp.py:478
+        w2m(g, bc[2], bc[3], lbx, lby);  // rp.py:480
+        int uo_x = ubx, uo_y = uby, free_cells = 0, nseg = 0, first_cell = 1, bad = 0;
+        line_aa_walk(ubx, uby, lbx, lby, [&](int x, int y) {
+            if (first_cell) { first_cell = 0; return true; }  // rp.py:494 skips the first cell (quirk Q4)
+            int xx = x < 0 ? x + g.W : x, yy = y < 0 ? y + g.H : y;
+            if (xx < 0 || yy < 0 || xx >= g.W || yy >= g.H) { bad = 1; return false; }
+            uint32_t wd;
+            if (STAGED) wd = srow[(yy - row0) * g.pitch_words + (xx >> 5)];
+            else wd = gsrc[(size_t)yy * g.pitch_words + (xx >> 5)];
+            const int v = (wd >> (xx & 31)) & 1u;
+            if (v) free_cells = 1;
+            if ((!v || (x == lbx && y == lby)) && free_cells) {
+                double ux, uy, lx, ly;
+                m2w(g, uo_x, uo_y, ux, uy);
+                m2w(g, x, y, lx, ly);
+                if (sqrt(sq(ux - lx) + sq(uy - ly)) > min_width) {  // rp.py:510
+                    if (nseg < kMaxSeg) segs[n * kMaxSeg + nseg] = make_short4((short)uo_x, (short)uo_y, (short)x, (short)y);
+                    ++nseg;
+                }
+                uo_x = x; uo_y = y;
+                free_cells = 0;
+            } else if (!v && !free_cells) {
+                uo_x = x; uo_y = y;
+            }
+            return true;
+        });
+        if (bad || nseg > kMaxSeg) status |= MPC_ST_INDEX_ERROR;
+        nsegs[n] = nseg;
+    }
+    __syncwarp();
+    if (nsegs[0] == 0 && lane == 0) status |= MPC_ST_NO_SEGMENT;  // rp.py:547 max([]) -> ValueError
+    status = __reduce_or_sync(0xffffffffu, status);
+    if (status) {
+        if (lane == 0 && flags) atomicOr(&flags[b], status | MPC_ST_DEAD);
+        return;
+    }
+    // ---- phase 2: waypoints whose pick does not depend on the previous one ----
+    for (int n = lane; n < N; n += 32) {
+        const int k = (first_w + n) % pv.n_wp;
+        const int nseg = nsegs[n];
+        if (n > 0 && nseg >= 2) continue;
+        double ubx, uby, lbx, lby;
+        if (nseg == 0) { ubx = pv.x[k]; uby = pv.y[k]; lbx = ubx; lby = uby; }  // rp.py:595
+        else {
+            int best = 0;
+            if (n == 0 && nseg > 1) {  // largest segment, first maximum (rp.py:545-548)
+                double bl = -1.0;
+                for (int i = 0; i < nseg; ++i) {
+                    const short4 s4 = segs[n * kMaxSeg + i];
+                    double ux, uy, lx, ly;
+                    m2w(g, s4.x, s4.y, ux, uy);
+                    m2w(g, s4.z, s4.w, lx, ly);
+                    const double l = sqrt(sq(ux - lx) + sq(uy - ly));
+                    if (l > bl) { bl = l; best = i; }
+                }
+            }
+            const short4 s4 = segs[n * kMaxSeg + best];
+            m2w(g, s4.x, s4.y, ubx, uby);
+            m2w(g, s4.z, s4.w, lbx, lby);
+        }
+        const RayOut o = finalize_wp(pv, k, ubx, uby, lbx, lby, sm);
+        ub_out[(size_t)b * N + n] = o.ub;
+        lb_out[(size_t)b * N + n] = o.lb;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) prev_cells[4 * n + i] = o.cells[i];
+        if (cells_sm_out)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cells_sm_out[((size_t)b * N + n) * 4 + i] = o.cells_sm[i];
+    }
+    __syncwarp();
+    // ---- phase 3: multi-candidate waypoints, in order (rp.py:552-586) ----
+    for (int n = 1; n < N; ++n) {
+        const int nseg = nsegs[n];  // warp-uniform
+        if (nseg < 2) continue;
+        const int k = (first_w + n) % pv.n_wp, kp = (first_w + n - 1) % pv.n_wp;
+        const double ds = pv.ds_next[kp];  // wp_prev - wp (rp.py:558)
+        const double upx = prev_cells[4 * (n - 1) + 0] + ds * pv.cos_psi[kp];  // rp.py:559
+        const double upy = prev_cells[4 * (n - 1) + 1] + ds * pv.cos_psi[kp];  // rp.py:560 (quirk Q2)
+        const double lpx = prev_cells[4 * (n - 1) + 2] + ds * pv.sin_psi[kp];  // rp.py:561
+        const double lpy = prev_cells[4 * (n - 1) + 3] + ds * pv.sin_psi[kp];  // rp.py:562
+        double md = INFINITY, ubx = 0, uby = 0, lbx = 0, lby = 0;
+        if (lane < nseg) {
+            const short4 s4 = segs[n * kMaxSeg + lane];
+            m2w(g, s4.x, s4.y, ubx, uby);
+            m2w(g, s4.z, s4.w, lbx, lby);
+            const double d_ub = sqrt(sq(ubx - upx) + sq(uby - upy));  // rp.py:576
+            const double d_lb = sqrt(sq(lbx - lpx) + sq(lby - lpy));  // rp.py:577
+            md = (d_ub + d_lb) / 2;
+        }
+        double wmd = md;
+        int wl = lane;
+#pragma unroll
+        for (int s = 4; s > 0; s >>= 1) {  // kMaxSeg = 8 candidates live in lanes 0..7
+            const double o = __shfl_xor_sync(0xffffffffu, wmd, s);
+            const int ol = __shfl_xor_sync(0xffffffffu, wl, s);
+            if (o < wmd || (o == wmd && ol < wl)) { wmd = o; wl = ol; }  // list.index(min()) = first minimum
+        }
+        wl = __shfl_sync(0xffffffffu, wl, 0);
+        if (lane == wl) {
+            const RayOut o = finalize_wp(pv, k, ubx, uby, lbx, lby, sm);
+            ub_out[(size_t)b * N + n] = o.ub;
+            lb_out[(size_t)b * N + n] = o.lb;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) prev_cells[4 * n + i] = o.cells[i];
+            if (cells_sm_out)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cells_sm_out[((size_t)b * N + n) * 4 + i] = o.cells_sm[i];
+        }
+        __syncwarp();
+    }
+}
+
+size_t raycast_smem_bytes(const GridView& g, int N, bool staged) {
+    size_t s = staged ? (size_t)g.H * g.pitch_words * 4 : 0;
+    s += (size_t)N * kMaxSeg * sizeof(short4) + (size_t)N * 4 * sizeof(double) + (size_t)((N + 1) & ~1) * sizeof(int) + 16;
+    return s;
+}
+
+void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridView& g, const PathView& pv,
+                    const int2* rowspan, const int* wp_id, int first_offset, int N, double min_width, double sm,
+                    double* ub, double* lb, double* cells_sm, int* flags, int B, bool staged, cudaStream_t st) {
+    const size_t smem = raycast_smem_bytes(g, N, staged);
+    if (staged) {
+        cudaFuncSetAttribute(raycast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        raycast_kernel<true><<<B, 32, smem, st>>>(grids, grid_stride_words, g, pv, rowspan, wp_id, first_offset, N,
+                                                  min_width, sm, ub, lb, cells_sm, flags, B);
+    } else {
+        cudaFuncSetAttribute(raycast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        raycast_kernel<false><<<B, 32, smem, st>>>(grids, grid_stride_words, g, pv, rowspan, wp_id, first_offset, N,
+                                                   min_width, sm, ub, lb, cells_sm, flags, B);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 front: SpatialBicycleModel.get_current_waypoint + t2s (sbm.py:256-279, 183-219)
+// ------------------------------------------------------------------------------------------------
+__global__ void localize_t2s_kernel(const double* __restrict__ state, int* __restrict__ wp_id,
+                                    double* __restrict__ spatial, int* __restrict__ flags, PathView pv, double length,
+                                    int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (flags && (flags[b] & (MPC_ST_DEAD | MPC_ST_FINISHED))) return;
+    const double x = state[b], y = state[(size_t)B + b], psi = state[2 * (size_t)B + b], s = state[3 * (size_t)B + b];
+    // first index with length_cum > s  (sbm.py:265-266); all-False -> IndexError in the reference
+    int lo = 0, hi = pv.n_wp;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pv.length_cum[mid] > s) hi = mid; else lo = mid + 1;
+    }
+    if (lo >= pv.n_wp || !(s < length)) {  // simulation.py:134 loop condition
+        if (flags) atomicOr(&flags[b], MPC_ST_FINISHED);
+        return;
+    }
+    const int next = lo, prev = next > 0 ? next - 1 : pv.n_wp - 1;  // index -1 wraps in numpy
+    const double s_next = pv.length_cum[next], s_prev = pv.length_cum[prev];
+    const int w = (fabs(s - s_next) < fabs(s - s_prev)) ? next : prev;  // strict <: ties -> prev (quirk Q8)
+    wp_id[b] = w;
+    const double e_y = pv.cos_psi[w] * (y - pv.y[w]) - pv.sin_psi[w] * (x - pv.x[w]);  // sbm.py:202-205
+    const double PI = 3.141592653589793;
+    double e_psi = psi - pv.psi[w];
+    e_psi = np_mod(e_psi + PI, 2 * PI) - PI;  // sbm.py:209
+    spatial[b] = e_y;
+    spatial[(size_t)B + b] = e_psi;
+}
+
+void launch_localize(const double* state, int* wp_id, double* spatial, int* flags, const PathView& pv, double length,
+                     int B, cudaStream_t st) {
+    localize_t2s_kernel<<<(B + 255) / 256, 256, 0, st>>>(state, wp_id, spatial, flags, pv, length, B);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 back: SpatialBicycleModel.drive (sbm.py:221-244), explicit Euler, in place
+// ------------------------------------------------------------------------------------------------
+__global__ void rollout_kernel(double* __restrict__ state, const double* __restrict__ spatial,
+                               const int* __restrict__ wp_id, const double* __restrict__ u, const int* __restrict__ flags,
+                               PathView pv, double L, double Ts, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (flags && (flags[b] & (MPC_ST_DEAD | MPC_ST_FINISHED))) return;
+    const double v = u[2 * (size_t)b], delta = u[2 * (size_t)b + 1];
+    const double psi = state[2 * (size_t)B + b];
+    const double x_dot = v * cos(psi);          // sbm.py:231
+    const double y_dot = v * sin(psi);          // sbm.py:232
+    const double psi_dot = v / L * tan(delta);  // sbm.py:233
+    state[b] += x_dot * Ts;                     // sbm.py:237
+    state[(size_t)B + b] += y_dot * Ts;
+    state[2 * (size_t)B + b] = psi + psi_dot * Ts;
+    const double e_y = spatial[b], e_psi = spatial[(size_t)B + b];
+    const double s_dot = 1 / (1 - e_y * pv.kappa[wp_id[b]]) * v * cos(e_psi);  // sbm.py:240
+    state[3 * (size_t)B + b] += s_dot * Ts;                                      // sbm.py:244
+}
+
+void launch_rollout(double* state, const double* spatial, const int* wp_id, const double* u, const int* flags,
+                    const PathView& pv, double L, double Ts, int B, cudaStream_t st) {
+    rollout_kernel<<<(B + 255) / 256, 256, 0, st>>>(state, spatial, wp_id, u, flags, pv, L, Ts, B);
+}
+
+// ------------------------------------------------------------------------------------------------
+// closed-loop statistics: per-scenario accumulation + final reduction
+// ------------------------------------------------------------------------------------------------
+__global__ void accumulate_stats_kernel(const int* __restrict__ flags, const int* __restrict__ iters,
+                                        const double* __restrict__ spatial, double* __restrict__ acc /*[4][B]*/, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int f = flags[b];
+    if (f & (MPC_ST_DEAD | MPC_ST_FINISHED)) return;
+    acc[b] += 1.0;                                         // scenario-steps (= QP solves)
+    acc[(size_t)B + b] += (double)iters[b];                // ADMM iterations
+    acc[2 * (size_t)B + b] += (f & MPC_ST_QP_FALLBACK) ? 1.0 : 0.0;
+    const double ey = fabs(spatial[b]);
+    acc[3 * (size_t)B + b] += ey;
+    acc[4 * (size_t)B + b] = fmax(acc[4 * (size_t)B + b], ey);
+}
+
+void launch_accumulate_stats(const int* flags, const int* iters, const double* spatial, double* acc, int B,
+                             cudaStream_t st) {
+    accumulate_stats_kernel<<<(B + 255) / 256, 256, 0, st>>>(flags, iters, spatial, acc, B);
+}
+
+}  // namespace mpcb
