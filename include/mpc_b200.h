@@ -46,6 +46,7 @@ extern "C" {
 
 /* per-scenario QP status: the OSQP status values the reference would see in dec.info.status_val */
 #define MPC_QP_SOLVED 1
+#define MPC_QP_SOLVED_INACCURATE 2 /* max_iter reached, residuals within 10x tolerances */
 #define MPC_QP_MAX_ITER (-2)
 #define MPC_QP_PRIMAL_INFEASIBLE (-3)
 #define MPC_QP_DUAL_INFEASIBLE (-4)
@@ -186,6 +187,15 @@ int mpc_scenarios_ptrs(mpc_engine *h, double **d_state, double **d_spatial, int3
 int mpc_scenarios_read(mpc_engine *h, double *h_state, double *h_control, double *h_u, int32_t *h_iters,
                        int32_t *h_qp_status, int32_t *h_flags, int32_t *h_infeas, int32_t *h_wp_id,
                        double *h_ub, double *h_lb);
+
+/* ---- ReferencePath.compute_speed_profile (rp.py:289-354), one-off, synchronous, no engine needed ---
+ * n = n_waypoints - 1 variables; h_li[n-1] distances between consecutive waypoints, h_vmax[n] the
+ * curvature-limited speed bound (rp.py:329-331); cfg supplies the OSQP settings (NULL = defaults).
+ * fp64 on the device; the iterates follow the reference solver's so that its eps = 1e-3 answer -- which
+ * becomes v_ref -- is reproduced, not merely the exact minimiser. */
+int mpc_speed_profile(const double *h_li, const double *h_vmax, int32_t n, double v_min, double a_min,
+                      double a_max, const mpc_config *cfg, double *h_v_out, int32_t *h_iters,
+                      int32_t *h_status);
 
 /* number of kernel launches enqueued by this engine since creation (bench.py's gpu_launches) */
 int64_t mpc_launch_count(mpc_engine *h);

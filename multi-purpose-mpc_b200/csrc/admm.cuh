@@ -65,7 +65,8 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(kFull, v, s);
     return v;
 }
-template <typename T> __device__ __forceinline__ T tabs(T v) { return v < T(0) ? -v : v; }
+__device__ __forceinline__ float tabs(float v) { return fabsf(v); }   // clears the sign of -0.0 too (redux.max on bits)
+__device__ __forceinline__ double tabs(double v) { return fabs(v); }
 template <typename T> __device__ __forceinline__ T tmax(T a, T b) { return a > b ? a : b; }
 template <typename T> __device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
 __device__ __forceinline__ float trsqrt(float v) { return 1.0f / sqrtf(v); }
@@ -553,10 +554,33 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
         }
     }
     if (status == 0) {
-        // max_iter reached: OSQP re-checks with 10x tolerances and may report "solved inaccurate"
-        // etc.; in every such case it RETURNS the iterate, so for the caller only -2 vs NaN matters.
-        status = -2;
+        // max_iter reached: OSQP re-checks the residuals with 10x looser tolerances ("approximate"
+        // termination) and reports solved-inaccurate (2) or max-iter (-2).  Either way it RETURNS
+        // the iterate, which is all the reference looks at (MPC.py:185-206).
         iter = st.max_iter;
+        T axd[3], axb[5], aty[5];
+        A_apply(s, x, lane, axd, axb);
+        At_apply(s, yd, yb, aty);
+        T pr_u = 0, nz_u = 0, nax_u = 0, du_u = 0, npx_u = 0, naty_u = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const T ei = T(1) / s.Ed[i];
+            pr_u = tmax(pr_u, tabs(axd[i] - zd[i]) * ei); nz_u = tmax(nz_u, tabs(zd[i]) * ei);
+            nax_u = tmax(nax_u, tabs(axd[i]) * ei);
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const T ei = T(1) / s.Eb[i], di = T(1) / s.D[i], px = s.P[i] * x[i];
+            pr_u = tmax(pr_u, tabs(axb[i] - zb[i]) * ei); nz_u = tmax(nz_u, tabs(zb[i]) * ei);
+            nax_u = tmax(nax_u, tabs(axb[i]) * ei);
+            du_u = tmax(du_u, tabs(px + s.q[i] + aty[i]) * di); npx_u = tmax(npx_u, tabs(px) * di);
+            naty_u = tmax(naty_u, tabs(aty[i]) * di);
+        }
+        pr_u = warp_max(pr_u); nz_u = warp_max(nz_u); nax_u = warp_max(nax_u);
+        du_u = warp_max(du_u) * cinv; npx_u = warp_max(npx_u); naty_u = warp_max(naty_u);
+        const T eps_prim = T(10) * T(st.eps_abs) + T(10) * T(st.eps_rel) * tmax(nz_u, nax_u);
+        const T eps_dual = T(10) * T(st.eps_abs) + T(10) * T(st.eps_rel) * cinv * tmax(tmax(nq_u, naty_u), npx_u);
+        status = (pr_u < eps_prim && du_u < eps_dual) ? 2 : -2;
     }
     const bool nan_out = (status == -3 || status == -4 || status == -7);
 #pragma unroll

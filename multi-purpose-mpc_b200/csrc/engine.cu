@@ -103,6 +103,8 @@ static void drop_graph(mpc_engine* h) {
     h->graph_B = 0;
 }
 
+extern "C" int mpc_set_error_(int code, const char* msg) { return fail(code, msg); }
+
 extern "C" {
 
 void mpc_config_default(mpc_config* c) {
