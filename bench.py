@@ -1,0 +1,321 @@
+"""bench.py -- headline benchmark of the B200 batched MPC engine.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--precision 0|1]
+  (N > 1: launched by torchrun, one rank per GPU; RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the env)
+
+Workload (BASELINE.json configs[1]): path tracking, 4096 independent cars per GPU on the sim track with
+randomised start waypoints / offsets (seed 2), horizon N = 30, reference weights and OSQP defaults
+(cold start, eps_abs = eps_rel = 1e-3).  A "step" is one closed-loop step of every car:
+localise + t2s -> grid raycast -> LTV assembly + ADMM QP solve -> rollout (MPC.get_control + car.drive of
+the reference, src/simulation.py:137-140), i.e. one QP solve per car.
+
+Prints ONE JSON line (rank 0).  `value` = QP solves/s of the whole job with state resident in HBM;
+`e2e` = the same through mpc_step_host (pinned host buffers, H2D + D2H inside the timed region);
+`roofline` for the dominant kernel (K1+K2 assemble + ADMM), `cpu_baseline` = the CPU oracle port (the
+reference's algorithm in C, all host cores) on a bounded sample of the same scenarios.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+N_HORIZON = 30
+METRIC = "mpc_qp_solves_per_sec_N30"
+UNIT = "QP solves/s"
+
+
+def load_track():
+    G = os.path.join(REPO, "tests", "golden")
+    T = np.load(os.path.join(G, "sim_track.npz"))
+    W = int(T["grid_shape"][1])
+    grid = np.unpackbits(T["grid_bits"], axis=1)[:, :W].astype(np.int8)
+    return T, grid
+
+
+def scenario_states(T, B, lo, hi, seed=2):
+    """C2 of SURVEY.md section 8d: all B scenarios are generated identically on every rank, then sliced."""
+    from mpc_b200 import distributed as D
+    sc = D.make_scenarios(len(T["wp_x"]), B, seed=seed)
+    w = sc["start_wp"][lo:hi]
+    e_y, e_psi = sc["e_y"][lo:hi], sc["e_psi"][lo:hi]
+    lc = np.cumsum(T["segment_lengths"])
+    x, y, psi = T["wp_x"][w], T["wp_y"][w], T["wp_psi"][w]
+    return np.ascontiguousarray(np.stack([x - e_y * np.sin(psi), y + e_y * np.cos(psi), psi + e_psi, lc[w]]))
+
+
+def flop_model(N, iters, n_factor=1):
+    """F_iter = 340N + 264, F_factor = 400(N+1), F_check = 142N + 78 (every 25 iterations)."""
+    f_iter, f_fac, f_chk = 340 * N + 264, 400 * (N + 1), 142 * N + 78
+    return iters * f_iter + n_factor * f_fac + (iters // 25) * f_chk
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+def cpu_oracle_world(T, grid):
+    from oracle import oracle as orc
+    pt = orc.PathTables(T["wp_x"], T["wp_y"], T["wp_psi"], T["wp_kappa"], T["wp_vref"], T["segment_lengths"],
+                        T["border"], True)
+    kmax = np.tan(0.66) / 0.12
+    cfg = orc.mpc_cfg(N_HORIZON, [1.0, 0.0, 0.0], [0.5, 0.0], [1.0, 0.0, 0.0], [-np.inf] * 3, [np.inf] * 3,
+                      [0.0, -kmax], [1.0, kmax], 4.0, 0.12, 0.06 / np.sqrt(2))
+    return orc, orc.World(pt, cfg, grid.shape, T["origin"], float(T["resolution"]), 0.05)
+
+
+def time_cpu_port(T, grid, states4xB, steps, threads=0):
+    """The oracle port (reference algorithm, C, fp64, OpenMP over scenarios) on `states`; returns
+    (solves/s, seconds, threads)."""
+    orc, world = cpu_oracle_world(T, grid)
+    B = states4xB.shape[1]
+    st = np.ascontiguousarray(states4xB.T.copy())
+    ctrl = np.zeros((B, 2 * N_HORIZON))
+    infeas = np.zeros(B, np.int32)
+    alive = np.ones(B, np.int32)
+    nthr = threads or orc.num_threads()
+    t0 = time.perf_counter()
+    stats = world.batch_closed_loop(grid, st, ctrl, infeas, alive, steps, nthr)
+    dt = time.perf_counter() - t0
+    return stats[1] / dt, dt, nthr, stats
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path.  The reference is pure Python + OSQP + scikit-image, none of
+    which exist on the GPU box, so this arm times the oracle port of the same algorithm (oracle/*.c: fp64,
+    one scenario per OpenMP thread, all host cores) on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    T, grid = load_track()
+    B = args.batch
+    sample = min(B, 1024)
+    states = scenario_states(T, B, 0, sample)
+    for _ in range(max(args.warmup, 0) and 1):
+        time_cpu_port(T, grid, states[:, :64], 1)
+    per_step = []
+    for _ in range(args.steps):
+        v, dt, nthr, _ = time_cpu_port(T, grid, states, 1)
+        per_step.append((v, dt))
+    value = float(np.mean([v for v, _ in per_step]))
+    ms = float(np.mean([dt for _, dt in per_step]) * 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "path tracking, %d cars/GPU on sim_map, randomised start offsets (seed 2), N=30; "
+                                   "reference arm steps a %d-car sample per step" % (B, sample),
+                       "horizon": N_HORIZON, "batch_per_gpu": B, "eps_abs": 1e-3, "eps_rel": 1e-3, "cold_start": True},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthr, "kind": "port",
+                             "sample": "%d cars x 1 closed-loop step per timed step, OpenMP over cars" % sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference = Python + OSQP + scikit-image, not installable offline; this arm is the C port of the "
+                    "same algorithm (oracle/), which is FASTER than the reference's Python (no interpreter, no scipy "
+                    "assembly at ~5 ms/step)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="scenarios per GPU")
+    ap.add_argument("--precision", type=int, default=0, help="0 = fp32 ADMM (production), 1 = fp64")
+    ap.add_argument("--cpu-sample", type=int, default=768, help="cars in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import mpc_b200
+    from mpc_b200 import _lib, distributed as D
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    T, grid = load_track()
+    Bg = args.batch * world                      # weak scaling: fixed work per GPU
+    lo, hi = D.shard_range(Bg, rank, world)
+    B = hi - lo
+    states = scenario_states(T, Bg, lo, hi)
+    tab = _lib.path_table(T["wp_x"], T["wp_y"], T["wp_psi"], T["wp_kappa"], T["wp_vref"])
+    lc = np.cumsum(T["segment_lengths"])
+
+    def make_engine():
+        e = mpc_b200.Engine(precision=args.precision)
+        e.set_path(tab, lc, T["border"], True)
+        e.set_base_grid(grid, T["origin"], float(T["resolution"]))
+        e.scenarios_init(states)
+        return e
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    # ---------------- device-resident arm: K timed steps, CUDA events per step, L2 flushed in between ----
+    eng = make_engine()
+    for _ in range(args.warmup):
+        eng.step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = eng.launch_count()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(float(k))
+        ev[k][0].record()
+        eng.step()
+        ev[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    sampler.stop_flag = True
+    launches = eng.launch_count() - l0
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    ms_total = D.max_over_ranks(float(np.sum(ms_steps)))
+    out = eng.scenarios_read()
+    iters_last = out["iters"].astype(np.int64)
+    live = ((out["flags"] & (2 | 32)) == 0)
+    n_live = int(live.sum())
+    value = Bg * args.steps / (ms_total * 1e-3)
+
+    # ---------------- per-kernel durations (same workload, events around every kernel) -----------------
+    eng.set_profiling(True)
+    eng.run_closed_loop(args.steps)
+    prof, nl = eng.get_profile()
+    kernel_ms = {k: v / max(n, 1) for (k, v), n in zip(prof.items(), nl)}
+    eng.set_profiling(False)
+    stats = eng.run_closed_loop(0)
+    out2 = eng.scenarios_read()
+    mean_iters = float(out2["iters"].mean())
+    flops_per_launch = float(sum(flop_model(N_HORIZON, int(i)) for i in out2["iters"]))
+    solve_ms = kernel_ms["assemble_solve"]
+    achieved = flops_per_launch / (solve_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # nominal: no measured FP32-pipe figure exists in MEASURED_PEAKS.json
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    rollout_gbs = 100.0 * B / (kernel_ms["rollout"] * 1e-3) / 1e9 if kernel_ms["rollout"] > 0 else None
+    eng.close()
+
+    # ---------------- end-to-end arm: host buffers, H2D + D2H inside the timed region -------------------
+    eng = make_engine()
+    hs = states.copy()
+    hu = np.zeros((B, 2))
+    hf = np.zeros(B, np.int32)
+    for _ in range(args.warmup):
+        eng.step_host(hs, hu, hf)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.step_host(hs, hu, hf)
+    barrier()
+    e2e_s = D.max_over_ranks(time.perf_counter() - t0)
+    e2e_value = Bg * args.steps / e2e_s
+    eng.close()
+
+    agg = D.allreduce_stats(stats)  # the one collective of the job: statistics only
+
+    # ---------------- CPU baseline: the oracle port on a bounded sample, rank 0, N = 1 only --------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = min(args.cpu_sample, B)
+        v, dt, nthr, _ = time_cpu_port(T, grid, states[:, :sample], 2)
+        cpu = {"value": v, "unit": UNIT, "cores": nthr, "kind": "port",
+               "sample": "%d of the %d cars x 2 closed-loop steps (%.1f s), oracle/*.c fp64, OpenMP over cars"
+                         % (sample, B, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == 0 else "f64", "data": "synthetic",
+            "config": {"workload": "path tracking, %d cars/GPU on sim_map, randomised start offsets (seed 2), N=30 "
+                                   "(BASELINE configs[1]); one step = localise+raycast+QP solve+rollout for every car" % args.batch,
+                       "horizon": N_HORIZON, "batch_per_gpu": args.batch, "global_batch": Bg, "eps_abs": 1e-3,
+                       "eps_rel": 1e-3, "cold_start": True, "l2": "flushed between timed steps (256 MB fill)",
+                       "parallelism": "scenario shards, no data-path collective"},
+            "closed_loop_steps_per_sec": value, "mean_admm_iters": mean_iters, "live_scenarios_rank0": n_live,
+            "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * B * 8),
+                    "d2h_bytes_per_step": int(6 * B * 8 + 4 * B)},
+            "gpu_launches": int(launches),
+            "kernel_ms": kernel_ms,
+            "roofline": {"kernel": "assemble_solve_kernel<float,5> (K1+K2)" if args.precision == 0 else "assemble_solve_kernel<double,5>",
+                         "bound": "fp32_pipe" if args.precision == 0 else "fp64_pipe", "achieved": achieved,
+                         "peak": fp32_peak if args.precision == 0 else fp32_peak / 2, "unit": "TFLOP/s",
+                         "frac": achieved / (fp32_peak if args.precision == 0 else fp32_peak / 2),
+                         "peak_source": "nominal 148 SM x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json has no CUDA-core figure)",
+                         "flops_per_launch": flops_per_launch, "traffic": None,
+                         "model": "SURVEY 8d: iters*(340N+264) + 400(N+1) + (iters/25)*(142N+78) per instance, actual iteration counts"},
+            "roofline_hbm": {"kernel": "rollout_kernel (K4)", "bound": "hbm", "achieved": rollout_gbs, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": (rollout_gbs / hbm_peak) if rollout_gbs else None,
+                             "bytes_per_instance": 100},
+            "clocks": sampler.summary(),
+            "stats": agg,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

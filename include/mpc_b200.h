@@ -79,8 +79,7 @@ typedef struct mpc_config {
     int32_t max_iter, scaling, check_termination, adaptive_rho_interval;
     double adaptive_rho_tolerance;
     /* engine choices */
-    int32_t precision;         /* 0 = fp32 ADMM (default), 1 = fp64 ADMM (validation path) */
-    int32_t refine;            /* iterative-refinement steps of the linear solve per ADMM iteration */
+    int32_t precision;         /* 0 = fp32 ADMM (default; use with eps >= 1e-4), 1 = fp64 ADMM (validation path) */
 } mpc_config;
 
 /* Fills cfg with the reference's defaults (src/simulation.py:100-119 and OSQP 0.6 defaults). */

@@ -30,7 +30,7 @@ class MpcConfig(C.Structure):
                 ("alpha", C.c_double), ("eps_abs", C.c_double), ("eps_rel", C.c_double),
                 ("eps_prim_inf", C.c_double), ("eps_dual_inf", C.c_double), ("max_iter", C.c_int32),
                 ("scaling", C.c_int32), ("check_termination", C.c_int32), ("adaptive_rho_interval", C.c_int32),
-                ("adaptive_rho_tolerance", C.c_double), ("precision", C.c_int32), ("refine", C.c_int32)]
+                ("adaptive_rho_tolerance", C.c_double), ("precision", C.c_int32)]
 
 
 EXPORTS = [

@@ -1,13 +1,24 @@
 // admm.cu -- kernel entry points for K1+K2 (see admm.cuh).  FMA contraction is enabled here: the QP
 // solution is compared within a tolerance, not bit-for-bit.
 #include "engine.h"
+#include <cstdio>
+#include <cstdlib>
 
 namespace mpcb {
 
 constexpr int kWarpsPerBlock = 2;
+// Tuning point per precision: RLEV = PCR levels kept in registers (the rest in shared memory),
+// MINB = minimum resident blocks per SM handed to __launch_bounds__ (caps registers per thread).
+template <typename T> struct Tune;
+template <> struct Tune<float> { static constexpr int rlev = 5, minb = 4; };
+template <> struct Tune<double> { static constexpr int rlev = 0, minb = 4; };
+template <int NLEV, int RLEV> constexpr int clamp_rlev() { return RLEV < NLEV ? RLEV : NLEV; }
+template <typename T, int NLEV, int RLEV> constexpr size_t smem_bytes() {
+    return (size_t)kWarpsPerBlock * (kConstRows + 18 * (NLEV - RLEV)) * 32 * sizeof(T);
+}
 
-template <typename T, int NLEV>
-__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+template <typename T, int NLEV, int RLEV, int MINB>
+__global__ void __launch_bounds__(32 * kWarpsPerBlock, MINB)
 solve_qp_kernel(int N, AdmmSettings st, const double* __restrict__ Pd, const double* __restrict__ q,
                 const double* __restrict__ Ax, const double* __restrict__ l, const double* __restrict__ u,
                 double* __restrict__ x_out, int* __restrict__ iters, int* __restrict__ status, int B) {
@@ -19,7 +30,9 @@ solve_qp_kernel(int N, AdmmSettings st, const double* __restrict__ Pd, const dou
     load_stage_qp<T>(s, N, lane, Pd + (size_t)b * n, q + (size_t)b * n, Ax + (size_t)b * nnz, l + (size_t)b * m,
                      u + (size_t)b * m);
     T w[5];
-    const SolveResult r = admm_solve<T, NLEV>(s, st, lane, N + 1, n, w);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sm = reinterpret_cast<T*>(smem_raw) + (size_t)(threadIdx.x >> 5) * smem_rows_per_warp<NLEV, RLEV>() * 32;
+    const SolveResult r = admm_solve<T, NLEV, RLEV>(s, st, lane, N + 1, n, sm, w);
     if (x_out && lane <= N) {
         double* xo = x_out + (size_t)b * n;
 #pragma unroll
@@ -32,8 +45,8 @@ solve_qp_kernel(int N, AdmmSettings st, const double* __restrict__ Pd, const dou
     }
 }
 
-template <typename T, int NLEV>
-__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+template <typename T, int NLEV, int RLEV, int MINB>
+__global__ void __launch_bounds__(32 * kWarpsPerBlock, MINB)
 assemble_solve_kernel(MpcParams mp, AdmmSettings st, PathView pv, const double* __restrict__ spatial,
                       const int* __restrict__ wp_id, double* __restrict__ control, const double* __restrict__ ub,
                       const double* __restrict__ lb, int* __restrict__ infeas, double* __restrict__ u_out,
@@ -50,7 +63,9 @@ assemble_solve_kernel(MpcParams mp, AdmmSettings st, PathView pv, const double* 
     assemble_stage<T>(s, mp, pv, lane, wp_id[b], spatial[b], spatial[(size_t)B + b], cc, ub + (size_t)b * N,
                       lb + (size_t)b * N);
     T w[5];
-    const SolveResult r = admm_solve<T, NLEV>(s, st, lane, N + 1, n, w);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sm = reinterpret_cast<T*>(smem_raw) + (size_t)(threadIdx.x >> 5) * smem_rows_per_warp<NLEV, RLEV>() * 32;
+    const SolveResult r = admm_solve<T, NLEV, RLEV>(s, st, lane, N + 1, n, sm, w);
     const bool ok = !(r.status == -3 || r.status == -4 || r.status == -7);  // OSQP returns x (MPC.py:185-206)
     if (x_out && lane <= N) {
         double* xo = x_out + (size_t)b * n;
@@ -87,36 +102,59 @@ assemble_solve_kernel(MpcParams mp, AdmmSettings st, PathView pv, const double* 
     }
 }
 
-template <typename T>
-static int solve_qp_dispatch(int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax,
-                             const double* l, const double* u, double* x_out, int* iters, int* status, int B,
-                             cudaStream_t s) {
+template <typename T, int NLEV, int RLEV, int MINB>
+static void solve_qp_launch(int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax,
+                            const double* l, const double* u, double* x_out, int* iters, int* status, int B,
+                            cudaStream_t s) {
+    constexpr int R = clamp_rlev<NLEV, RLEV>();
     const int grid = (B + kWarpsPerBlock - 1) / kWarpsPerBlock, block = 32 * kWarpsPerBlock;
-    if (N + 1 <= 16) solve_qp_kernel<T, 4><<<grid, block, 0, s>>>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B);
-    else if (N + 1 <= 32) solve_qp_kernel<T, 5><<<grid, block, 0, s>>>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B);
-    else return MPC_E_UNSUPPORTED;
-    return 0;
+    const size_t smem = smem_bytes<T, NLEV, R>();
+    cudaFuncSetAttribute(solve_qp_kernel<T, NLEV, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    solve_qp_kernel<T, NLEV, R, MINB><<<grid, block, smem, s>>>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B);
 }
+
+template <typename T, int NLEV, int RLEV, int MINB>
+static void assemble_solve_launch(const MpcParams& mp, const AdmmSettings& st, const PathView& pv, const double* spatial,
+                                  const int* wp_id, double* control, const double* ub, const double* lb, int* infeas,
+                                  double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
+                                  cudaStream_t s) {
+    constexpr int R = clamp_rlev<NLEV, RLEV>();
+    const int grid = (B + kWarpsPerBlock - 1) / kWarpsPerBlock, block = 32 * kWarpsPerBlock;
+    const size_t smem = smem_bytes<T, NLEV, R>();
+    cudaFuncSetAttribute(assemble_solve_kernel<T, NLEV, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    assemble_solve_kernel<T, NLEV, R, MINB><<<grid, block, smem, s>>>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas,
+                                                                      u_out, x_out, iters, qp_status, flags, B);
+}
+
+#ifdef MPC_TUNING_VARIANTS
+// development only: extra fp32 instantiations of the QP-only kernel selected with MPC_TUNE="rlev,minb"
+static bool tuned_solve_qp(int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax,
+                           const double* l, const double* u, double* x_out, int* iters, int* status, int B,
+                           cudaStream_t s) {
+    const char* e = getenv("MPC_TUNE");
+    if (!e || N + 1 <= 16) return false;
+    int r = 5, m = 4;
+    sscanf(e, "%d,%d", &r, &m);
+#define V(R_, M_) if (r == R_ && m == M_) { solve_qp_launch<float, 5, R_, M_>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s); return true; }
+    V(5, 5) V(5, 6) V(3, 6) V(3, 8) V(2, 8) V(0, 8) V(0, 10)
+#undef V
+    return false;
+}
+#endif
 
 int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax,
                     const double* l, const double* u, double* x_out, int* iters, int* status, int B, cudaStream_t s) {
-    if (precision == 1) return solve_qp_dispatch<double>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s);
-    return solve_qp_dispatch<float>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s);
-}
-
-template <typename T>
-static int assemble_solve_dispatch(const MpcParams& mp, const AdmmSettings& st, const PathView& pv, const double* spatial,
-                                   const int* wp_id, double* control, const double* ub, const double* lb, int* infeas,
-                                   double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
-                                   cudaStream_t s) {
-    const int grid = (B + kWarpsPerBlock - 1) / kWarpsPerBlock, block = 32 * kWarpsPerBlock;
-    if (mp.N + 1 <= 16)
-        assemble_solve_kernel<T, 4><<<grid, block, 0, s>>>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out,
-                                                           x_out, iters, qp_status, flags, B);
-    else if (mp.N + 1 <= 32)
-        assemble_solve_kernel<T, 5><<<grid, block, 0, s>>>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out,
-                                                           x_out, iters, qp_status, flags, B);
-    else return MPC_E_UNSUPPORTED;
+    if (N + 1 > 32) return MPC_E_UNSUPPORTED;
+    if (precision == 1) {
+        if (N + 1 <= 16) solve_qp_launch<double, 4, Tune<double>::rlev, Tune<double>::minb>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s);
+        else solve_qp_launch<double, 5, Tune<double>::rlev, Tune<double>::minb>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s);
+        return 0;
+    }
+#ifdef MPC_TUNING_VARIANTS
+    if (tuned_solve_qp(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s)) return 0;
+#endif
+    if (N + 1 <= 16) solve_qp_launch<float, 4, Tune<float>::rlev, Tune<float>::minb>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s);
+    else solve_qp_launch<float, 5, Tune<float>::rlev, Tune<float>::minb>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s);
     return 0;
 }
 
@@ -124,11 +162,12 @@ int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings
                           const double* spatial, const int* wp_id, double* control, const double* ub, const double* lb,
                           int* infeas, double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
                           cudaStream_t s) {
-    if (precision == 1)
-        return assemble_solve_dispatch<double>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters,
-                                               qp_status, flags, B, s);
-    return assemble_solve_dispatch<float>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters,
-                                          qp_status, flags, B, s);
+    if (mp.N + 1 > 32) return MPC_E_UNSUPPORTED;
+#define GO(T_, L_) assemble_solve_launch<T_, L_, Tune<T_>::rlev, Tune<T_>::minb>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s)
+    if (precision == 1) { if (mp.N + 1 <= 16) GO(double, 4); else GO(double, 5); }
+    else { if (mp.N + 1 <= 16) GO(float, 4); else GO(float, 5); }
+#undef GO
+    return 0;
 }
 
 }  // namespace mpcb

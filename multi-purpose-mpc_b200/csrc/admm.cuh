@@ -10,6 +10,9 @@
 // stages: the two inputs of a stage are eliminated locally (their 2x2 block is diagonal), and the
 // remaining chain of 3x3 blocks is solved by parallel cyclic reduction (log2(32) = 5 levels), so
 // one linear solve is ~40 shuffles + ~130 FMAs per lane instead of a 31-step serial Riccati sweep.
+// The iteration is written in increment form (see admm_solve) so that fp32 reproduces OSQP's
+// iteration counts and infeasibility certificates at the reference's default tolerance; fp64 is
+// the validation path (and the one to use for eps < 1e-4).
 // Norms for termination / rho adaptation are warp reductions (redux.sync on the float bit pattern
 // for fp32).  No tensor cores: per-instance 3x3 / 5x5 blocks are not a dense contraction.
 #pragma once
@@ -30,7 +33,7 @@ constexpr unsigned kFull = 0xffffffffu;
 
 struct AdmmSettings {
     double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, adaptive_rho_tolerance;
-    int max_iter, scaling, check_termination, adaptive_rho_interval, refine;
+    int max_iter, scaling, check_termination, adaptive_rho_interval;
 };
 
 struct MpcParams {  // MPC.__init__ arguments (MPC.py:15-59) + car geometry
@@ -92,13 +95,26 @@ template <typename T> struct Stage {
     int ctype[5];    // -1 loose, 0 inequality, 1 equality (bound rows; dynamics rows are always 1)
 };
 
-template <typename T, int NLEV> struct Factor {
-    T al[NLEV][9], be[NLEV][9];
+// PCR factor.  Levels [0, RLEV) live in registers, levels [RLEV, NLEV) in shared memory laid out
+// [coefficient][lane] (conflict-free, one 128 B / 256 B wavefront per coefficient); the split trades
+// registers (occupancy) against shared-memory bandwidth and is chosen per precision at compile time.
+template <typename T, int NLEV, int RLEV> struct Factor {
+    T al[RLEV > 0 ? RLEV : 1][9], be[RLEV > 0 ? RLEV : 1][9];
+    T* fs;                 // this warp's shared slab: [(NLEV - RLEV) * 18][32]
     T Dinv[6];             // symmetric: 00 01 02 11 12 22
     T iv, ik;              // 1 / S_vv, 1 / S_kk
     T sxv0, sxv2, sxk0, sxk1;  // S_xu nonzeros
     T fv, fk;              // coupling of (v, kappa)_j to (t, e_psi)_{j+1}
 };
+
+// per-warp shared constants (read only at termination checks / first iteration): [16][32]
+//   0..2 d | 3..7 D | 8..10 Ed | 11..15 Eb
+constexpr int kConstRows = 16;
+template <int NLEV, int RLEV> __host__ __device__ constexpr int smem_rows_per_warp() { return kConstRows + 18 * (NLEV - RLEV); }
+
+template <typename T> __device__ __forceinline__ T tfma(T a, T b, T c);
+template <> __device__ __forceinline__ float tfma<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> __device__ __forceinline__ double tfma<double>(double a, double b, double c) { return fma(a, b, c); }
 
 // z = A w for this lane: zd (dynamics block j) and zb (bound rows)
 template <typename T>
@@ -216,9 +232,9 @@ template <typename T> __device__ __forceinline__ void inv3sym(const T* M, T* R) 
 }
 
 // Build S = P + sigma I + A' R A for this lane's stage, eliminate the inputs, PCR-factorise.
-template <typename T, int NLEV>
-__device__ __forceinline__ void factorize(const Stage<T>& s, Factor<T, NLEV>& f, T sigma, T rd, const T rb[5], int lane,
-                                          int nstage) {
+template <typename T, int NLEV, int RLEV>
+__device__ __forceinline__ void factorize(const Stage<T>& s, Factor<T, NLEV, RLEV>& f, T sigma, T rd, const T rb[5],
+                                          int lane, int nstage) {
     const T* a = s.a;
     T diag[5];
 #pragma unroll
@@ -307,41 +323,51 @@ __device__ __forceinline__ void factorize(const Stage<T>& s, Factor<T, NLEV>& f,
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
             Lo[i] = -t1[i]; U[i] = -t2[i];
-            f.al[lev][i] = al[i]; f.be[lev][i] = be[i];
+            if (lev < RLEV) { f.al[lev < RLEV ? lev : 0][i] = al[i]; f.be[lev < RLEV ? lev : 0][i] = be[i]; }
+            else { f.fs[((lev - RLEV) * 18 + i) * 32 + lane] = al[i]; f.fs[((lev - RLEV) * 18 + 9 + i) * 32 + lane] = be[i]; }
         }
     }
     T Di[9];
     inv3sym(Dm, Di);
     f.Dinv[0] = Di[0]; f.Dinv[1] = Di[1]; f.Dinv[2] = Di[2]; f.Dinv[3] = Di[4]; f.Dinv[4] = Di[5]; f.Dinv[5] = Di[8];
+    __syncwarp();
 }
 
 // x = S^-1 b
-template <typename T, int NLEV>
-__device__ __forceinline__ void kkt_solve(const Factor<T, NLEV>& f, const T b[5], int lane, T x[5]) {
-    T bv = f.iv * b[3], bk = f.ik * b[4];
-    T bx0 = b[0] - bv * f.sxv0 - bk * f.sxk0;
-    T bx1 = b[1] - bk * f.sxk1;
-    T bx2 = b[2] - bv * f.sxv2;
+template <typename T, int NLEV, int RLEV>
+__device__ __forceinline__ void kkt_solve(const Factor<T, NLEV, RLEV>& f, const T b[5], int lane, T x[5]) {
+    const T bv = f.iv * b[3], bk = f.ik * b[4];
+    T bx0 = tfma(-bk, f.sxk0, tfma(-bv, f.sxv0, b[0]));
+    T bx1 = tfma(-bk, f.sxk1, b[1]);
+    T bx2 = tfma(-bv, f.sxv2, b[2]);
     T t1 = shfl_up(bk * f.fk, 1), t2 = shfl_up(bv * f.fv, 1);
     if (lane > 0) { bx1 -= t1; bx2 -= t2; }
 #pragma unroll
     for (int lev = 0; lev < NLEV; ++lev) {
         const int sft = 1 << lev;
-        T u0 = shfl_up(bx0, sft), u1 = shfl_up(bx1, sft), u2 = shfl_up(bx2, sft);
-        T d0 = shfl_dn(bx0, sft), d1 = shfl_dn(bx1, sft), d2 = shfl_dn(bx2, sft);
-        const T* al = f.al[lev];
-        const T* be = f.be[lev];
-        T n0 = bx0 - (al[0] * u0 + al[1] * u1 + al[2] * u2) - (be[0] * d0 + be[1] * d1 + be[2] * d2);
-        T n1 = bx1 - (al[3] * u0 + al[4] * u1 + al[5] * u2) - (be[3] * d0 + be[4] * d1 + be[5] * d2);
-        T n2 = bx2 - (al[6] * u0 + al[7] * u1 + al[8] * u2) - (be[6] * d0 + be[7] * d1 + be[8] * d2);
-        bx0 = n0; bx1 = n1; bx2 = n2;
+        const T u0 = shfl_up(bx0, sft), u1 = shfl_up(bx1, sft), u2 = shfl_up(bx2, sft);
+        const T d0 = shfl_dn(bx0, sft), d1 = shfl_dn(bx1, sft), d2 = shfl_dn(bx2, sft);
+        T al[9], be[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            if (lev < RLEV) { al[i] = f.al[lev < RLEV ? lev : 0][i]; be[i] = f.be[lev < RLEV ? lev : 0][i]; }
+            else { al[i] = f.fs[((lev - RLEV) * 18 + i) * 32 + lane]; be[i] = f.fs[((lev - RLEV) * 18 + 9 + i) * 32 + lane]; }
+        }
+        // two independent FMA chains per row (up / down neighbours) keep the dependent depth at 3
+        const T p0 = tfma(-al[2], u2, tfma(-al[1], u1, tfma(-al[0], u0, bx0)));
+        const T q0 = tfma(be[2], d2, tfma(be[1], d1, be[0] * d0));
+        const T p1 = tfma(-al[5], u2, tfma(-al[4], u1, tfma(-al[3], u0, bx1)));
+        const T q1 = tfma(be[5], d2, tfma(be[4], d1, be[3] * d0));
+        const T p2 = tfma(-al[8], u2, tfma(-al[7], u1, tfma(-al[6], u0, bx2)));
+        const T q2 = tfma(be[8], d2, tfma(be[7], d1, be[6] * d0));
+        bx0 = p0 - q0; bx1 = p1 - q1; bx2 = p2 - q2;
     }
-    x[0] = f.Dinv[0] * bx0 + f.Dinv[1] * bx1 + f.Dinv[2] * bx2;
-    x[1] = f.Dinv[1] * bx0 + f.Dinv[3] * bx1 + f.Dinv[4] * bx2;
-    x[2] = f.Dinv[2] * bx0 + f.Dinv[4] * bx1 + f.Dinv[5] * bx2;
-    T xn1 = shfl_dn(x[1], 1), xn2 = shfl_dn(x[2], 1);  // fv, fk are 0 where there is no successor
-    x[3] = f.iv * (b[3] - f.sxv0 * x[0] - f.sxv2 * x[2] - f.fv * xn2);
-    x[4] = f.ik * (b[4] - f.sxk0 * x[0] - f.sxk1 * x[1] - f.fk * xn1);
+    x[0] = tfma(f.Dinv[2], bx2, tfma(f.Dinv[1], bx1, f.Dinv[0] * bx0));
+    x[1] = tfma(f.Dinv[4], bx2, tfma(f.Dinv[3], bx1, f.Dinv[1] * bx0));
+    x[2] = tfma(f.Dinv[5], bx2, tfma(f.Dinv[4], bx1, f.Dinv[2] * bx0));
+    const T xn1 = shfl_dn(x[1], 1), xn2 = shfl_dn(x[2], 1);  // fv, fk are 0 where there is no successor
+    x[3] = f.iv * tfma(-f.fv, xn2, tfma(-f.sxv2, x[2], tfma(-f.sxv0, x[0], b[3])));
+    x[4] = f.ik * tfma(-f.fk, xn1, tfma(-f.sxk1, x[1], tfma(-f.sxk0, x[0], b[4])));
 }
 
 template <typename T> __device__ __forceinline__ void set_rho(const Stage<T>& s, T rho, T& rd, T rb[5], T rbi[5]) {
@@ -357,11 +383,19 @@ struct SolveResult {
     int iters, status;
 };
 
-// The OSQP loop for one scenario (all 32 lanes of the warp call this together).
+// The OSQP loop for one scenario (all 32 lanes of the warp call this together), in "increment form":
+// instead of x~ the linear solve returns D = x~ - x,
+//     S D = -(q + P x + A'(y + R r)),      r = A x - z  (tracked, never recomputed from x),
+// and the row updates use  v - z = alpha (r + A D),  z+ = clip(z + (v - z) + y / rho),
+// dy = rho ((v - z) - (z+ - z)),  r+ = r + alpha A D - (z+ - z).  This is the same iteration as
+// oracle/osqp_oracle.c in exact arithmetic (tools/admm_pcr_model.py checks it), but every quantity
+// that multiplies rho_eq = 1e3 rho is a small residual rather than a difference of O(1) numbers, which
+// is what lets the fp32 path reproduce OSQP's iteration counts and infeasibility certificates.
 // On return w[5] holds the UNSCALED primal stage vector (NaN when OSQP would return no solution).
-template <typename T, int NLEV>
+// sm: this warp's shared slab, smem_rows_per_warp<NLEV, RLEV>() * 32 elements of T.
+template <typename T, int NLEV, int RLEV>
 __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSettings& st, int lane, int nstage, int nvar,
-                                                  T w[5]) {
+                                                  T* sm, T w[5]) {
     if (st.scaling > 0) ruiz_scale(s, st.scaling, nvar);
     else {
 #pragma unroll
@@ -374,88 +408,85 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
 #pragma unroll
     for (int i = 0; i < 5; ++i)
         s.ctype[i] = (s.lo[i] < -thr && s.hi[i] > thr) ? -1 : ((s.hi[i] - s.lo[i] < T(kRhoTol)) ? 1 : 0);
+    // constants that are only needed at checks go to shared memory
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { sm[i * 32 + lane] = s.d[i]; sm[(8 + i) * 32 + lane] = s.Ed[i]; }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { sm[(3 + i) * 32 + lane] = s.D[i]; sm[(11 + i) * 32 + lane] = s.Eb[i]; }
     T rho = T(st.rho), rd, rb[5], rbi[5];
-    const T sigma = T(st.sigma), alpha = T(st.alpha), oma = T(1) - T(st.alpha);
+    const T sigma = T(st.sigma), alpha = T(st.alpha);
     set_rho(s, rho, rd, rb, rbi);
-    Factor<T, NLEV> f;
-    factorize<T, NLEV>(s, f, sigma, rd, rb, lane, nstage);
+    Factor<T, NLEV, RLEV> f;
+    f.fs = sm + kConstRows * 32;
+    factorize<T, NLEV, RLEV>(s, f, sigma, rd, rb, lane, nstage);
     // constant norms
     T nq_s = T(0), nq_u = T(0);
 #pragma unroll
     for (int i = 0; i < 5; ++i) { nq_s = tmax(nq_s, tabs(s.q[i])); nq_u = tmax(nq_u, tabs(s.q[i] / s.D[i])); }
     nq_s = warp_max(nq_s); nq_u = warp_max(nq_u);
     const T cinv = T(1) / s.cs;
-
-    T x[5] = {0, 0, 0, 0, 0}, zd[3] = {0, 0, 0}, zb[5] = {0, 0, 0, 0, 0};
-    T yd[3] = {0, 0, 0}, yb[5] = {0, 0, 0, 0, 0};
+    // the loop keeps only a, c, e, P, q, lo, hi of the stage live
+    T x[5] = {0, 0, 0, 0, 0}, zb[5] = {0, 0, 0, 0, 0}, yd[3] = {0, 0, 0}, yb[5] = {0, 0, 0, 0, 0};
+    T rdy[3] = {0, 0, 0}, rbd[5] = {0, 0, 0, 0, 0};  // tracked residuals A x - z
     int status = 0, iter = 0;
+    int chk = st.check_termination > 0 ? st.check_termination : -1;
+    int adp = st.adaptive_rho_interval > 0 ? st.adaptive_rho_interval : -1;
     for (iter = 1; iter <= st.max_iter; ++iter) {
-        T rhs[5], td[3], tb[5], xt[5];
+        T g[5], td[3], tb[5], dl[5];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) td[i] = rd * zd[i] - yd[i];
+        for (int i = 0; i < 3; ++i) td[i] = tfma(rd, rdy[i], yd[i]);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) tb[i] = rb[i] * zb[i] - yb[i];
-        At_apply(s, td, tb, rhs);
+        for (int i = 0; i < 5; ++i) tb[i] = tfma(rb[i], rbd[i], yb[i]);
+        At_apply(s, td, tb, g);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) rhs[i] += sigma * x[i] - s.q[i];
-        kkt_solve<T, NLEV>(f, rhs, lane, xt);
-        for (int r = 0; r < st.refine; ++r) {  // iterative refinement: xt += S^-1 (rhs - S xt)
-            T rzd[3], rzb[5], sx[5], res[5], dxr[5];
-            A_apply(s, xt, lane, rzd, rzb);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) rzd[i] *= rd;
-#pragma unroll
-            for (int i = 0; i < 5; ++i) rzb[i] *= rb[i];
-            At_apply(s, rzd, rzb, sx);
-#pragma unroll
-            for (int i = 0; i < 5; ++i) res[i] = rhs[i] - (sx[i] + (s.P[i] + sigma) * xt[i]);
-            kkt_solve<T, NLEV>(f, res, lane, dxr);
-#pragma unroll
-            for (int i = 0; i < 5; ++i) xt[i] += dxr[i];
-        }
-        T ztd[3], ztb[5];
-        A_apply(s, xt, lane, ztd, ztb);
+        for (int i = 0; i < 5; ++i) g[i] = -(tfma(s.P[i], x[i], s.q[i]) + g[i]);
+        kkt_solve<T, NLEV, RLEV>(f, g, lane, dl);
+        T add[3], adb[5];
+        A_apply(s, dl, lane, add, adb);
         T dx[5], dyd[3], dyb[5];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            T xn = alpha * xt[i] + oma * x[i];
-            dx[i] = xn - x[i];
-            x[i] = xn;
-        }
+        for (int i = 0; i < 5; ++i) { dx[i] = alpha * dl[i]; x[i] += dx[i]; }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            T v = alpha * ztd[i] + oma * zd[i];
-            T zn = s.d[i];  // projection onto the equality
-            dyd[i] = rd * (v - zn);
+            const T wv = alpha * (rdy[i] + add[i]);          // v - z_prev
+            const T step = iter == 1 ? sm[i * 32 + lane] : T(0);  // z jumps from the cold start 0 to d once
+            dyd[i] = rd * (wv - step);
             yd[i] += dyd[i];
-            zd[i] = zn;
+            rdy[i] = tfma(alpha, add[i], rdy[i]) - step;
         }
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            T v = alpha * ztb[i] + oma * zb[i];
-            T zn = tmin(tmax(v + rbi[i] * yb[i], s.lo[i]), s.hi[i]);
-            dyb[i] = rb[i] * (v - zn);
+            const T wv = alpha * (rbd[i] + adb[i]);
+            const T zn = tmin(tmax(tfma(rbi[i], yb[i], zb[i] + wv), s.lo[i]), s.hi[i]);
+            const T step = zn - zb[i];
+            dyb[i] = rb[i] * (wv - step);
             yb[i] += dyb[i];
+            rbd[i] = tfma(alpha, adb[i], rbd[i]) - step;
             zb[i] = zn;
         }
-        const bool can_check = st.check_termination && (iter % st.check_termination == 0);
-        const bool can_adapt = st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0);
+        const bool can_check = (--chk == 0), can_adapt = (--adp == 0);
+        if (can_check) chk = st.check_termination;
+        if (can_adapt) adp = st.adaptive_rho_interval;
         if (can_check || can_adapt) {
-            T axd[3], axb[5], aty[5];
+            T axd[3], axb[5], aty[5], zd[3], D[5], Ed[3], Eb[5];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { zd[i] = sm[i * 32 + lane]; Ed[i] = sm[(8 + i) * 32 + lane]; }
+#pragma unroll
+            for (int i = 0; i < 5; ++i) { D[i] = sm[(3 + i) * 32 + lane]; Eb[i] = sm[(11 + i) * 32 + lane]; }
             A_apply(s, x, lane, axd, axb);
             At_apply(s, yd, yb, aty);
             // scaled and unscaled infinity norms
             T pr_s = 0, pr_u = 0, nz_s = 0, nz_u = 0, nax_s = 0, nax_u = 0;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                T r = tabs(axd[i] - zd[i]), ei = T(1) / s.Ed[i];
+                T r = tabs(axd[i] - zd[i]), ei = T(1) / Ed[i];
                 pr_s = tmax(pr_s, r); pr_u = tmax(pr_u, r * ei);
                 nz_s = tmax(nz_s, tabs(zd[i])); nz_u = tmax(nz_u, tabs(zd[i]) * ei);
                 nax_s = tmax(nax_s, tabs(axd[i])); nax_u = tmax(nax_u, tabs(axd[i]) * ei);
             }
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
-                T r = tabs(axb[i] - zb[i]), ei = T(1) / s.Eb[i];
+                T r = tabs(axb[i] - zb[i]), ei = T(1) / Eb[i];
                 pr_s = tmax(pr_s, r); pr_u = tmax(pr_u, r * ei);
                 nz_s = tmax(nz_s, tabs(zb[i])); nz_u = tmax(nz_u, tabs(zb[i]) * ei);
                 nax_s = tmax(nax_s, tabs(axb[i])); nax_u = tmax(nax_u, tabs(axb[i]) * ei);
@@ -463,7 +494,7 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
             T du_s = 0, du_u = 0, npx_s = 0, npx_u = 0, naty_s = 0, naty_u = 0;
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
-                T px = s.P[i] * x[i], di = T(1) / s.D[i];
+                T px = s.P[i] * x[i], di = T(1) / D[i];
                 T r = tabs(px + s.q[i] + aty[i]);
                 du_s = tmax(du_s, r); du_u = tmax(du_u, r * di);
                 npx_s = tmax(npx_s, tabs(px)); npx_u = tmax(npx_u, tabs(px) * di);
@@ -484,8 +515,8 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
                     T pyb[5], ndy = 0, lhs = 0;
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
-                        ndy = tmax(ndy, tabs(s.Ed[i] * dyd[i]));
-                        lhs += s.d[i] * dyd[i];  // u*max(dy,0) + l*min(dy,0) with l = u
+                        ndy = tmax(ndy, tabs(Ed[i] * dyd[i]));
+                        lhs += zd[i] * dyd[i];  // u*max(dy,0) + l*min(dy,0) with l = u = d
                     }
 #pragma unroll
                     for (int i = 0; i < 5; ++i) {
@@ -493,7 +524,7 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
                         if (s.hi[i] > thr) d = (s.lo[i] < -thr) ? T(0) : tmin(d, T(0));
                         else if (s.lo[i] < -thr) d = tmax(d, T(0));
                         pyb[i] = d;
-                        ndy = tmax(ndy, tabs(s.Eb[i] * d));
+                        ndy = tmax(ndy, tabs(Eb[i] * d));
                         lhs += s.hi[i] * tmax(d, T(0)) + s.lo[i] * tmin(d, T(0));
                     }
                     ndy = warp_max(ndy);
@@ -502,7 +533,7 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
                         T atdy[5], na = 0;
                         At_apply(s, dyd, pyb, atdy);
 #pragma unroll
-                        for (int i = 0; i < 5; ++i) na = tmax(na, tabs(atdy[i] / s.D[i]));
+                        for (int i = 0; i < 5; ++i) na = tmax(na, tabs(atdy[i] / D[i]));
                         na = warp_max(na);
                         pinf = na < epi * ndy;
                     }
@@ -511,13 +542,13 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
                     const T edi = T(st.eps_dual_inf);
                     T ndx = 0, qdx = 0;
 #pragma unroll
-                    for (int i = 0; i < 5; ++i) { ndx = tmax(ndx, tabs(s.D[i] * dx[i])); qdx += s.q[i] * dx[i]; }
+                    for (int i = 0; i < 5; ++i) { ndx = tmax(ndx, tabs(D[i] * dx[i])); qdx += s.q[i] * dx[i]; }
                     ndx = warp_max(ndx);
                     qdx = warp_sum(qdx);
                     if (ndx > edi && qdx < -s.cs * edi * ndx) {
                         T npdx = 0;
 #pragma unroll
-                        for (int i = 0; i < 5; ++i) npdx = tmax(npdx, tabs(s.P[i] * dx[i] / s.D[i]));
+                        for (int i = 0; i < 5; ++i) npdx = tmax(npdx, tabs(s.P[i] * dx[i] / D[i]));
                         npdx = warp_max(npdx);
                         if (npdx < s.cs * edi * ndx) {
                             T adxd[3], adxb[5];
@@ -525,12 +556,12 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
                             int bad = 0;
 #pragma unroll
                             for (int i = 0; i < 3; ++i) {
-                                T v = adxd[i] / s.Ed[i];
+                                T v = adxd[i] / Ed[i];
                                 if (v > edi * ndx || v < -edi * ndx) bad = 1;  // equality rows have finite bounds
                             }
 #pragma unroll
                             for (int i = 0; i < 5; ++i) {
-                                T v = adxb[i] / s.Eb[i];
+                                T v = adxb[i] / Eb[i];
                                 if ((s.hi[i] < thr && v > edi * ndx) || (s.lo[i] > -thr && v < -edi * ndx)) bad = 1;
                             }
                             dinf = !__any_sync(kFull, bad);
@@ -548,11 +579,14 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
                 if (rnew > rho * T(st.adaptive_rho_tolerance) || rnew < rho / T(st.adaptive_rho_tolerance)) {
                     rho = rnew;
                     set_rho(s, rho, rd, rb, rbi);
-                    factorize<T, NLEV>(s, f, sigma, rd, rb, lane, nstage);
+                    factorize<T, NLEV, RLEV>(s, f, sigma, rd, rb, lane, nstage);
                 }
             }
         }
     }
+    T D[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) D[i] = sm[(3 + i) * 32 + lane];
     if (status == 0) {
         // max_iter reached: OSQP re-checks the residuals with 10x looser tolerances ("approximate"
         // termination) and reports solved-inaccurate (2) or max-iter (-2).  Either way it RETURNS
@@ -564,13 +598,13 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
         T pr_u = 0, nz_u = 0, nax_u = 0, du_u = 0, npx_u = 0, naty_u = 0;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const T ei = T(1) / s.Ed[i];
-            pr_u = tmax(pr_u, tabs(axd[i] - zd[i]) * ei); nz_u = tmax(nz_u, tabs(zd[i]) * ei);
+            const T ei = T(1) / sm[(8 + i) * 32 + lane], zdi = sm[i * 32 + lane];
+            pr_u = tmax(pr_u, tabs(axd[i] - zdi) * ei); nz_u = tmax(nz_u, tabs(zdi) * ei);
             nax_u = tmax(nax_u, tabs(axd[i]) * ei);
         }
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            const T ei = T(1) / s.Eb[i], di = T(1) / s.D[i], px = s.P[i] * x[i];
+            const T ei = T(1) / sm[(11 + i) * 32 + lane], di = T(1) / D[i], px = s.P[i] * x[i];
             pr_u = tmax(pr_u, tabs(axb[i] - zb[i]) * ei); nz_u = tmax(nz_u, tabs(zb[i]) * ei);
             nax_u = tmax(nax_u, tabs(axb[i]) * ei);
             du_u = tmax(du_u, tabs(px + s.q[i] + aty[i]) * di); npx_u = tmax(npx_u, tabs(px) * di);
@@ -584,7 +618,7 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
     }
     const bool nan_out = (status == -3 || status == -4 || status == -7);
 #pragma unroll
-    for (int i = 0; i < 5; ++i) w[i] = nan_out ? T(NAN) : s.D[i] * x[i];
+    for (int i = 0; i < 5; ++i) w[i] = nan_out ? T(NAN) : D[i] * x[i];
     SolveResult r;
     r.iters = iter;
     r.status = status;

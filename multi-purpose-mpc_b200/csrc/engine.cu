@@ -94,7 +94,7 @@ static void refresh_params(mpc_engine* h) {
     s.eps_prim_inf = c.eps_prim_inf; s.eps_dual_inf = c.eps_dual_inf;
     s.adaptive_rho_tolerance = c.adaptive_rho_tolerance;
     s.max_iter = c.max_iter; s.scaling = c.scaling; s.check_termination = c.check_termination;
-    s.adaptive_rho_interval = c.adaptive_rho_interval; s.refine = c.refine;
+    s.adaptive_rho_interval = c.adaptive_rho_interval;
 }
 
 static void drop_graph(mpc_engine* h) {
@@ -120,7 +120,6 @@ void mpc_config_default(mpc_config* c) {
     c->eps_prim_inf = 1e-4; c->eps_dual_inf = 1e-4; c->max_iter = 4000; c->scaling = 10;
     c->check_termination = 25; c->adaptive_rho_interval = 25; c->adaptive_rho_tolerance = 5.0;
     c->precision = 0;
-    c->refine = 1;
 }
 
 const char* mpc_last_error(void) { return g_err.c_str(); }
@@ -130,7 +129,6 @@ static int validate_cfg(const mpc_config* c) {
     if (c->N < 3 || c->N > 31) return fail(MPC_E_UNSUPPORTED, "horizon N must be in [3, 31] in this build");
     if (!(c->car_length > 0) || !(c->Ts > 0)) return fail(MPC_E_INVALID, "car_length and Ts must be positive");
     if (c->precision != 0 && c->precision != 1) return fail(MPC_E_INVALID, "precision must be 0 (fp32) or 1 (fp64)");
-    if (c->refine < 0 || c->refine > 4) return fail(MPC_E_INVALID, "refine must be in [0, 4]");
     if (c->max_iter < 1 || c->check_termination < 0 || c->adaptive_rho_interval < 0 || c->scaling < 0)
         return fail(MPC_E_INVALID, "bad OSQP settings");
     return 0;

@@ -257,7 +257,7 @@ extern "C" int mpc_speed_profile(const double* h_li, const double* h_vmax, int32
     st.rho = c.rho; st.sigma = c.sigma; st.alpha = c.alpha; st.eps_abs = c.eps_abs; st.eps_rel = c.eps_rel;
     st.eps_prim_inf = c.eps_prim_inf; st.eps_dual_inf = c.eps_dual_inf; st.adaptive_rho_tolerance = c.adaptive_rho_tolerance;
     st.max_iter = c.max_iter; st.scaling = c.scaling; st.check_termination = c.check_termination;
-    st.adaptive_rho_interval = c.adaptive_rho_interval; st.refine = 0;
+    st.adaptive_rho_interval = c.adaptive_rho_interval;
     double *d_li = nullptr, *d_vmax = nullptr, *d_v = nullptr;
     int* d_info = nullptr;
     const int nt = 256;

@@ -35,7 +35,10 @@
 
 static int g_pow_mode = 0; /* 0: x*x (IEEE), 1: libm pow(x,2.0) as CPython/numpy do */
 void orc_set_pow_mode(int m) { g_pow_mode = m; }
-static inline double sq(double x) { return g_pow_mode ? pow(x, 2.0) : x * x; }
+/* through a volatile pointer: gcc folds a literal pow(x, 2.0) into x*x at -O2, which is exactly the
+ * substitution this switch exists to expose */
+static double (*volatile libm_pow)(double, double) = pow;
+static inline double sq(double x) { return g_pow_mode ? libm_pow(x, 2.0) : x * x; }
 
 /* numpy floor-mod for doubles (np.mod), b > 0 here */
 static inline double np_mod(double a, double b)

@@ -1,0 +1,304 @@
+"""GPU tier: the CUDA path, through the C ABI, against the oracle and the golden vectors.
+
+Bars (BASELINE.json north_star):
+  grid cells / drivable widths : bit-exact (integer decisions) -- widths bit-exact against the oracle in
+                                 IEEE mode and within 1 ulp of the reference-run golden (libm pow, see
+                                 oracle/mpc_oracle.c header)
+  QP primal                    : |x - x_oracle|_inf <= 1e-3 per instance; fp64 path at eps = 1e-5 and 1e-3,
+                                 fp32 path at the reference's own eps = 1e-3; identical status / iteration count
+  rollout                      : <= 1e-6 relative over one lap given identical controls
+"""
+import numpy as np
+import pytest
+
+from conftest import fixed_pattern, load_golden, sim_cfg, ulps
+
+pytestmark = pytest.mark.gpu
+QP_TOL = 1e-3  # north_star: per-instance max-norm
+
+
+def _dev():
+    import torch
+    return torch.device("cuda:0")
+
+
+def _t(a, dtype=None):
+    import torch
+    return torch.tensor(np.ascontiguousarray(a), dtype=dtype or torch.float64, device=_dev())
+
+
+# ------------------------------------------------------------------ K2: QP-only -------------------
+@pytest.mark.parametrize("precision,eps", [(1, 1e-5), (1, 1e-3), (0, 1e-3)])
+def test_qp_matches_oracle(orc, precision, eps):
+    import torch
+    import mpc_b200
+    TF, C1 = load_golden("teacher_forced.npz"), load_golden("c1_lap.npz")
+    Pd, q, Ax, l, u = (np.concatenate([TF["qp_" + k], C1["qp_" + k]]) for k in ("Pd", "q", "Ax", "l", "u"))
+    B, n = Pd.shape[0], 153
+    Ap, Ai = fixed_pattern(30)
+    xo, ito, sto = orc.batch_qp_solve(30, Pd, q, Ap, Ai, Ax, l, u, eps_abs=eps, eps_rel=eps)
+    eng = mpc_b200.Engine(precision=precision, eps_abs=eps, eps_rel=eps)
+    x = torch.zeros((B, n), dtype=torch.float64, device=_dev())
+    it = torch.zeros(B, dtype=torch.int32, device=_dev())
+    st = torch.zeros(B, dtype=torch.int32, device=_dev())
+    eng.solve_qp(_t(Pd), _t(q), _t(Ax), _t(l), _t(u), x, it, st)
+    eng.sync()
+    x, it, st = x.cpu().numpy(), it.cpu().numpy(), st.cpu().numpy()
+    eng.close()
+    assert np.array_equal(st, sto), "status differs from the oracle"
+    assert np.array_equal(it, ito), "iteration counts differ from the oracle"
+    ok = sto > 0
+    assert ok.sum() >= 60 and (~ok).sum() >= 6          # the fixture contains infeasible QPs too
+    assert np.isnan(x[~ok]).all()                        # OSQP returns no solution there (MPC.py:208)
+    d = np.abs(x[ok] - xo[ok]).max(axis=1)
+    assert d.max() <= (QP_TOL if precision == 0 else 1e-4), d.max()
+
+
+def test_qp_fp64_kkt_certificate_at_full_batch(orc):
+    """Size-independent property at BASELINE size (4096 QPs): every solved instance satisfies the
+    optimality conditions computed in fp64 from (P, q, A, l, u) alone; replicated inputs give replicated
+    outputs."""
+    import torch
+    import mpc_b200
+    from scipy import sparse
+    TF = load_golden("teacher_forced.npz")
+    B0, B = TF["qp_Pd"].shape[0], 4096
+    idx = np.arange(B) % B0
+    eng = mpc_b200.Engine(precision=1)
+    x = torch.zeros((B, 153), dtype=torch.float64, device=_dev())
+    it = torch.zeros(B, dtype=torch.int32, device=_dev())
+    st = torch.zeros(B, dtype=torch.int32, device=_dev())
+    eng.solve_qp(*[_t(TF["qp_" + k][idx]) for k in ("Pd", "q", "Ax", "l", "u")], x, it, st)
+    eng.sync()
+    x, it, st = x.cpu().numpy(), it.cpu().numpy(), st.cpu().numpy()
+    eng.close()
+    for b in range(B0, B):
+        assert st[b] == st[b % B0] and it[b] == it[b % B0]
+    assert np.array_equal(np.nan_to_num(x[B0:2 * B0]), np.nan_to_num(x[:B0]))
+    Ap, Ai = fixed_pattern(30)
+    for b in range(0, B0, 4):
+        if st[b] != 1:
+            continue
+        A = sparse.csc_matrix((TF["qp_Ax"][b], Ai, Ap), shape=(246, 153))
+        Ax_ = A @ x[b]
+        lo, hi = TF["qp_l"][b], TF["qp_u"][b]
+        viol = max(np.max(np.maximum(lo - Ax_, 0)), np.max(np.maximum(Ax_ - hi, 0)))
+        assert viol <= 1e-3 * (1 + np.abs(Ax_).max())
+
+
+# ------------------------------------------------------------------ K3b / rasteriser / K3 ----------
+def test_static_width_bit_exact(engine_factory, track, orc, orc_path):
+    eng = engine_factory(grid="free", border=False, precision=1)
+    ub, lb, border = eng.compute_width(0.23)
+    orc.set_pow_mode(False)
+    st, ub_o, lb_o, border_o = orc.compute_width(track.grid, track.origin, track.res, orc_path, 0.23)
+    assert st == 0
+    assert np.array_equal(border, border_o) and np.array_equal(ub, ub_o) and np.array_equal(lb, lb_o)  # vs oracle: exact
+    assert np.array_equal(border, track.border)                                                        # cells vs reference run
+    assert ulps(ub, track.wp_ub).max() <= 1 and ulps(lb, track.wp_lb).max() <= 1                       # widths vs libm pow
+
+
+def test_rasteriser_bit_exact(engine_factory, track):
+    R = load_golden("raycast_random.npz")
+    eng = engine_factory(grid="free")
+    eng.set_obstacles(R["obs"], R["obs_off"])
+    W = track.grid.shape[1]
+    gb = np.unpackbits(R["grid_bits"], axis=2)[:, :, :W].astype(np.int8)
+    for s in range(gb.shape[0]):
+        assert np.array_equal(eng.get_grid(s), gb[s])
+
+
+def test_raycast_bit_exact(engine_factory, track, orc, orc_path):
+    import torch
+    R = load_golden("raycast_random.npz")
+    eng = engine_factory(grid="free")
+    eng.set_obstacles(R["obs"], R["obs_off"])
+    nsc = len(R["obs_off"]) - 1
+    W = track.grid.shape[1]
+    grids = np.unpackbits(R["grid_bits"], axis=2)[:, :, :W].astype(np.int8)
+    sm = 0.06 / np.sqrt(2)
+    orc.set_pow_mode(False)
+    for c, (s, w, ok) in enumerate(R["wp_id"]):
+        wid = torch.zeros(nsc, dtype=torch.int32, device=_dev())
+        wid[s] = int(w)
+        ub = torch.zeros((nsc, 30), dtype=torch.float64, device=_dev())
+        lb = torch.zeros_like(ub)
+        cells = torch.zeros((nsc, 30, 4), dtype=torch.float64, device=_dev())
+        fl = torch.zeros(nsc, dtype=torch.int32, device=_dev())
+        eng.raycast(wid, ub, lb, cells, fl)
+        eng.sync()
+        st, ub_o, lb_o, cells_o = orc.update_path_constraints(grids[s], track.origin, track.res, orc_path, int(w) + 1,
+                                                              30, 2 * sm, sm)
+        assert (int(fl[s].item()) == 0) == (st == 0)
+        if st == 0:
+            u_, l_ = ub[s].cpu().numpy(), lb[s].cpu().numpy()
+            assert np.array_equal(u_, ub_o) and np.array_equal(l_, lb_o)             # vs oracle: bit-exact
+            assert np.array_equal(cells[s].cpu().numpy(), cells_o)
+            assert ulps(u_, R["ub"][c]).max() <= 1 and ulps(l_, R["lb"][c]).max() <= 1  # vs reference run (libm pow)
+
+
+def test_raycast_no_free_segment_is_flagged(engine_factory, track):
+    """rp.py:547: max([]) -> ValueError in the reference; a status bit here."""
+    import torch
+    import mpc_b200
+    eng = engine_factory(grid="free")
+    # block the whole corridor at waypoint 51 with one big disc
+    obs = np.array([[track.wp_x[51], track.wp_y[51], 0.3]])
+    eng.set_obstacles(obs, np.array([0, 1], np.int32))
+    wid = _t([50], torch.int32)
+    ub = torch.zeros((1, 30), dtype=torch.float64, device=_dev())
+    lb = torch.zeros_like(ub)
+    fl = torch.zeros(1, dtype=torch.int32, device=_dev())
+    eng.raycast(wid, ub, lb, None, fl)
+    eng.sync()
+    assert int(fl[0].item()) & mpc_b200.ST_NO_SEGMENT
+
+
+def test_staged_and_direct_raycast_agree(engine_factory, track):
+    """TMA-staged rows (horizon N = engine N) and the direct global-memory walk (other N) give the same bits."""
+    import torch
+    eng = engine_factory()
+    sm = 0.06 / np.sqrt(2)
+    wid = _t(np.arange(0, 200, 7), torch.int32)
+    B = wid.shape[0]
+    out = {}
+    for N in (30, 29):
+        ub = torch.zeros((B, N), dtype=torch.float64, device=_dev())
+        lb = torch.zeros_like(ub)
+        fl = torch.zeros(B, dtype=torch.int32, device=_dev())
+        eng.update_path_constraints(wid, 1, N, 2 * sm, sm, ub, lb, None, fl)
+        eng.sync()
+        out[N] = (ub.cpu().numpy(), lb.cpu().numpy())
+    assert np.array_equal(out[30][0][:, :29], out[29][0]) and np.array_equal(out[30][1][:, :29], out[29][1])
+
+
+# ------------------------------------------------------------------ full step, teacher forced -------
+@pytest.mark.parametrize("precision", [1, 0])
+def test_teacher_forced_step(engine_factory, precision):
+    TF = load_golden("teacher_forced.npz")
+    eng = engine_factory(precision=precision)
+    B = TF["state"].shape[0]
+    eng.scenarios_init(np.ascontiguousarray(TF["state"].T))
+    eng.scenarios_set_state(np.ascontiguousarray(TF["state"].T), np.ascontiguousarray(TF["control"]), None)
+    eng.step()
+    o = eng.scenarios_read()
+    assert np.array_equal(o["wp_id"], TF["wp_id"])
+    assert ulps(o["ub"], TF["ub"]).max() <= 1 and ulps(o["lb"], TF["lb"]).max() <= 1
+    assert np.array_equal(o["qp_status"], TF["status"]) and np.array_equal(o["iters"], TF["iters"])
+    ok = TF["status"] == 1
+    assert ((o["flags"] & 1) == (~ok).astype(np.int32)).all()          # fallback exactly where OSQP was infeasible
+    tol = QP_TOL if precision == 0 else 1e-8
+    assert np.abs(o["u"] - TF["u"]).max() <= tol
+    assert np.abs(o["control"] - TF["control_after"]).max() <= tol
+    rel = np.abs(o["state"].T - TF["state_after"]) / np.maximum(np.abs(TF["state_after"]), 1e-3)
+    assert rel.max() <= (1e-4 if precision == 0 else 1e-9)
+
+
+def test_rollout_one_lap_given_identical_controls(engine_factory):
+    """north_star: rollout state within 1e-6 relative over one lap given identical control sequences."""
+    import torch
+    C1 = load_golden("c1_lap.npz")
+    eng = engine_factory()
+    state = _t(C1["state"][0].reshape(4, 1))
+    worst = 0.0
+    for k in range(C1["state"].shape[0]):
+        eng.rollout(state, _t(C1["spatial"][k][:2].reshape(2, 1)), _t([C1["wp_id"][k]], torch.int32),
+                    _t(C1["u"][k].reshape(1, 2)), None)
+        ref = C1["state_after"][k]
+        got = state[:, 0].cpu().numpy()
+        worst = max(worst, np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3)))
+    assert worst <= 1e-6, worst
+
+
+def test_c1_closed_loop_free_running_fp64(engine_factory):
+    """The reference's default run (src/simulation.py), free running for the whole lap: the fp64 path follows
+    the reference's own trajectory (189 steps, including its 4 infeasible steps) to 1e-6."""
+    C1 = load_golden("c1_lap.npz")
+    eng = engine_factory(precision=1)
+    eng.scenarios_init(np.ascontiguousarray(C1["state"][0].reshape(4, 1)))
+    for k in range(C1["state"].shape[0]):
+        eng.step()
+        o = eng.scenarios_read()
+        assert o["iters"][0] == C1["iters"][k] and o["qp_status"][0] == C1["status"][k], k
+        assert np.abs(o["state"][:, 0] - C1["state_after"][k]).max() <= 1e-6, k
+    eng.step()  # s >= length now: the reference's while loop ends (simulation.py:134)
+    assert eng.scenarios_read()["flags"][0] & 32
+
+
+def test_c1_closed_loop_fp32_completes_the_lap(engine_factory):
+    """fp32 production path, free running: same number of steps to finish the lap, bounded tracking error."""
+    C1 = load_golden("c1_lap.npz")
+    eng = engine_factory(precision=0)
+    eng.scenarios_init(np.ascontiguousarray(C1["state"][0].reshape(4, 1)))
+    stats = eng.run_closed_loop(C1["state"].shape[0] + 20)
+    o = eng.scenarios_read()
+    assert o["flags"][0] & 32 and not (o["flags"][0] & 2)
+    assert abs(stats["scenario_steps"] - C1["state"].shape[0]) <= 2
+    assert stats["max_abs_ey"] <= np.abs(C1["spatial"][:, 0]).max() + 0.02
+
+
+def test_closed_loop_graph_equals_stepwise(engine_factory):
+    """mpc_run_closed_loop (CUDA graph) == repeated mpc_step; host-buffer step == device step."""
+    TF = load_golden("teacher_forced.npz")
+    st0 = np.ascontiguousarray(TF["state"].T)
+    a, b = engine_factory(precision=1), engine_factory(precision=1)
+    a.scenarios_init(st0); b.scenarios_init(st0)
+    a.run_closed_loop(5)
+    for _ in range(5):
+        b.step()
+    oa, ob = a.scenarios_read(), b.scenarios_read()
+    for k in ("state", "control", "u", "iters", "qp_status", "flags", "wp_id"):
+        assert np.array_equal(oa[k], ob[k]), k
+    c = engine_factory(precision=1)
+    c.scenarios_init(st0)
+    hs, hu = st0.copy(), np.zeros((st0.shape[1], 2))
+    for _ in range(5):
+        c.step_host(hs, hu)
+    assert np.array_equal(hs, oa["state"]) and np.array_equal(hu, oa["u"])
+
+
+def test_batch_properties_at_c2_size(engine_factory, track):
+    """BASELINE config 2 size (4096 cars): permutation equivariance and replica consistency of a full step."""
+    from mpc_b200 import distributed as D
+    B = 4096
+    sc = D.make_scenarios(track.n_wp, B, seed=2)
+    w = sc["start_wp"]
+    st = np.stack([track.wp_x[w] - sc["e_y"] * np.sin(track.wp_psi[w]), track.wp_y[w] + sc["e_y"] * np.cos(track.wp_psi[w]),
+                   track.wp_psi[w] + sc["e_psi"], track.length_cum[w]])
+    eng = engine_factory(grid="free", precision=0)
+    eng.scenarios_init(st)
+    eng.step()
+    o1 = eng.scenarios_read()
+    perm = np.random.default_rng(0).permutation(B)
+    eng.scenarios_init(np.ascontiguousarray(st[:, perm]))
+    eng.step()
+    o2 = eng.scenarios_read()
+    for k in ("state",):
+        assert np.array_equal(o1[k][:, perm], o2[k])
+    for k in ("u", "iters", "qp_status", "wp_id", "ub", "lb"):
+        assert np.array_equal(o1[k][perm], o2[k]), k
+    assert (o1["qp_status"] == 1).mean() > 0.9
+    assert (o1["u"][:, 0] > 0).all() and (np.abs(o1["u"][:, 1]) <= 0.66 + 1e-6).all()
+
+
+def test_speed_profile_matches_reference(track):
+    """ReferencePath.compute_speed_profile (rp.py:289-354) on the device vs the reference-run golden v_ref."""
+    from mpc_b200.speed_profile import solve_speed_profile
+    n = track.n_wp - 1
+    li = np.array([((track.wp_x[i + 1] - track.wp_x[i]) ** 2 + (track.wp_y[i + 1] - track.wp_y[i]) ** 2) ** 0.5
+                   for i in range(n)])
+    vmax = np.minimum(1.0, np.sqrt(4.0 / (np.abs(track.wp_kappa[:n]) + 1e-12)))
+    v, it, st = solve_speed_profile(li, vmax, 0.0, -0.1, 0.5, return_info=True)
+    assert st == 1
+    assert np.abs(v - track.wp_vref[:n]).max() <= 1e-9
+
+
+def test_errors_are_reported_not_swallowed(track):
+    import mpc_b200
+    eng = mpc_b200.Engine()
+    import torch
+    with pytest.raises(mpc_b200.MpcError, match="mpc_set_path"):
+        eng.raycast(_t([0], torch.int32), _t(np.zeros((1, 30))), _t(np.zeros((1, 30))))
+    with pytest.raises(mpc_b200.MpcError):
+        mpc_b200.Engine(N=64)   # horizons above 31 stages are not built yet: loud, not silent
+    eng.close()

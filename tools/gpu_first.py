@@ -35,7 +35,7 @@ def run(eng, Pd, q, Ax, l, u):
 
 
 for prec, refine, eps in ((1, 0, 1e-3), (1, 0, 1e-5), (0, 1, 1e-3), (0, 0, 1e-3), (0, 1, 1e-5)):
-    eng = mpc_b200.Engine(precision=prec, refine=refine, eps_abs=eps, eps_rel=eps)
+    eng = mpc_b200.Engine(precision=prec, eps_abs=eps, eps_rel=eps)
     x, it, st = run(eng, Pd, q, Ax, l, u)
     key = "prec%d_ref%d_eps%g" % (prec, refine, eps)
     out[key] = dict(iters=it.tolist(), status=st.tolist())
@@ -68,7 +68,7 @@ for key in list(out.keys()):
 
 # timing: replicate the 48 QPs to a large batch
 for prec, refine in ((0, 1), (0, 0), (1, 0)):
-    eng = mpc_b200.Engine(precision=prec, refine=refine)
+    eng = mpc_b200.Engine(precision=prec)
     B = 148 * 8 * 16 if prec == 0 else 148 * 8 * 4
     rep = (B + B0 - 1) // B0
     big = [np.tile(a, (rep, 1))[:B] for a in (Pd, q, Ax, l, u)]

@@ -26,7 +26,7 @@ def ulps(a, b):
 
 
 # ---- static width (K3b) on the obstacle-free map
-eng = mpc_b200.Engine(precision=1, refine=0)
+eng = mpc_b200.Engine(precision=1)
 eng.set_path(tab, lc, None, True)
 eng.set_base_grid(grid, origin, res)
 ub, lb, border = eng.compute_width(0.23)
@@ -74,7 +74,7 @@ eng.close()
 # ---- teacher-forced steps (all four kernels) fp64
 TF = np.load(os.path.join(G, "teacher_forced.npz"))
 for prec, refine in ((1, 0), (0, 1)):
-    eng = mpc_b200.Engine(precision=prec, refine=refine)
+    eng = mpc_b200.Engine(precision=prec)
     eng.set_path(tab, lc, T["border"], True)
     eng.set_base_grid(grid_obs, origin, res)
     B = TF["state"].shape[0]
@@ -95,7 +95,7 @@ for prec, refine in ((1, 0), (0, 1)):
 # ---- C1 closed loop, free running, fp64 vs the reference lap
 C1 = np.load(os.path.join(G, "c1_lap.npz"))
 for prec, refine in ((1, 0), (0, 1)):
-    eng = mpc_b200.Engine(precision=prec, refine=refine)
+    eng = mpc_b200.Engine(precision=prec)
     eng.set_path(tab, lc, T["border"], True)
     eng.set_base_grid(grid_obs, origin, res)
     st0 = np.ascontiguousarray(C1["state"][0].reshape(4, 1))
