@@ -43,7 +43,9 @@ def load_track():
 def scenario_states(T, B, lo, hi, seed=2):
     """C2 of SURVEY.md section 8d: all B scenarios are generated identically on every rank, then sliced."""
     from mpc_b200 import distributed as D
-    sc = D.make_scenarios(len(T["wp_x"]), B, seed=seed)
+    # start waypoints U{0..119}: 80 waypoints (3.5 m = 70+ steps at 1 m/s) of headroom before s >= length would
+    # end a car's lap (simulation.py:134), so every car is live in every timed step
+    sc = D.make_scenarios(len(T["wp_x"]), B, seed=seed, max_start_wp=len(T["wp_x"]) - 80)
     w = sc["start_wp"][lo:hi]
     e_y, e_psi = sc["e_y"][lo:hi], sc["e_psi"][lo:hi]
     lc = np.cumsum(T["segment_lengths"])
@@ -228,6 +230,9 @@ def main():
     iters_last = out["iters"].astype(np.int64)
     live = ((out["flags"] & (2 | 32)) == 0)
     n_live = int(live.sum())
+    if n_live != B:
+        print("WARNING: %d of %d cars finished / died during the timed region; value counts them as work" % (B - n_live, B),
+              file=sys.stderr)
     value = Bg * args.steps / (ms_total * 1e-3)
 
     # ---------------- per-kernel durations (same workload, events around every kernel) -----------------

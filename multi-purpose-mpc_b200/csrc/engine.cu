@@ -61,7 +61,7 @@ struct mpc_engine {
     bool have_grid = false;
     DevBuf<int2> d_rowspan;
     bool rowspan_valid = false;
-    bool staged = true;
+    int max_rows = 0;
     DevBuf<int> d_err;
     // scenarios (engine-owned closed loop)
     int B = 0;
@@ -234,8 +234,7 @@ static int compute_rowspan(mpc_engine* h) {
     CUDA_OK(cudaMemcpyAsync(h->d_rowspan.p, rs.data(), n * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
     h->rowspan_valid = true;
-    // staging needs the whole grid's worth of shared memory in the worst case
-    h->staged = raycast_smem_bytes(h->g, N, true) <= 200 * 1024;
+    h->max_rows = max_rows;
     return 0;
 }
 
@@ -394,10 +393,9 @@ int mpc_update_path_constraints(mpc_engine* h, const int32_t* d_wp_id, int32_t f
     const uint32_t* grids = h->grids_B ? h->d_grids.p : h->d_base.p;
     const size_t stride = h->grids_B ? (size_t)h->words : 0;
     // the row-span table is built for the engine's own horizon (first waypoint wp_id+1, N = cfg.N)
-    const bool staged = h->staged && h->rowspan_valid && N == h->cfg.N;
-    if (raycast_smem_bytes(h->g, N, staged) > 200 * 1024) return fail(MPC_E_UNSUPPORTED, "horizon too long for shared memory");
-    launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, d_wp_id, first_offset, N, min_width, safety_margin, d_ub,
-                   d_lb, d_cells_sm, d_flags, B, staged, h->stream);
+    const bool rowspan_ok = h->rowspan_valid && N == h->cfg.N && first_offset == 1;
+    launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, d_wp_id, first_offset, N, min_width,
+                   safety_margin, d_ub, d_lb, d_cells_sm, d_flags, B, rowspan_ok, h->stream);
     ++h->launches;
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -505,8 +503,8 @@ static int enqueue_step(mpc_engine* h, bool with_stats, bool timed) {
     const double sm = h->cfg.car_width / std::sqrt(2.0);
     const uint32_t* grids = h->grids_B ? h->d_grids.p : h->d_base.p;
     const size_t stride = h->grids_B ? (size_t)h->words : 0;
-    launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm, h->s_ub.p,
-                   h->s_lb.p, nullptr, h->s_flags.p, B, h->staged && h->rowspan_valid, s);
+    launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm,
+                   h->s_ub.p, h->s_lb.p, nullptr, h->s_flags.p, B, h->rowspan_valid, s);
     if (timed) cudaEventRecord(h->ev[2], s);
     int r = launch_assemble_solve(h->cfg.precision, h->mp, h->st, h->pv, h->s_spatial.p, h->s_wp_id.p, h->s_control.p,
                                   h->s_ub.p, h->s_lb.p, h->s_infeas.p, h->s_u.p, nullptr, h->s_iters.p,

@@ -18,10 +18,12 @@ void launch_rasterize(const uint32_t* base, uint32_t* grids, int words, const Gr
                       const int* offsets, int B, cudaStream_t st);
 void launch_compute_width(const uint32_t* grid, const GridView& g, const PathView& pv, double max_width, double* ub,
                           double* lb, double* border, int* err, cudaStream_t st);
-size_t raycast_smem_bytes(const GridView& g, int N, bool staged);
+int raycast_plan(const GridView& g, int N, bool shared_grid, int max_rows, bool rowspan_ok, int* warps, int* stage_rows,
+                 size_t* smem);
 void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridView& g, const PathView& pv,
-                    const int2* rowspan, const int* wp_id, int first_offset, int N, double min_width, double sm,
-                    double* ub, double* lb, double* cells_sm, int* flags, int B, bool staged, cudaStream_t st);
+                    const int2* rowspan, int max_rows, const int* wp_id, int first_offset, int N, double min_width,
+                    double sm, double* ub, double* lb, double* cells_sm, int* flags, int B, bool rowspan_ok,
+                    cudaStream_t st);
 void launch_localize(const double* state, int* wp_id, double* spatial, int* flags, const PathView& pv, double length,
                      int B, cudaStream_t st);
 void launch_rollout(double* state, const double* spatial, const int* wp_id, const double* u, const int* flags,

@@ -187,192 +187,320 @@ __device__ __forceinline__ RayOut finalize_wp(const PathView& pv, int k, double 
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <bool STAGED>
-__global__ void __launch_bounds__(32)
-raycast_kernel(const uint32_t* __restrict__ grids, size_t grid_stride_words, GridView g, PathView pv,
-               const int2* __restrict__ rowspan /*[n_wp]: rows touched by a horizon starting at wp*/,
-               const int* __restrict__ wp_id, int first_offset, int N, double min_width, double sm,
-               double* __restrict__ ub_out, double* __restrict__ lb_out, double* __restrict__ cells_sm_out,
-               int* __restrict__ flags, int B) {
+// TMA bulk copy global -> shared (cp.async.bulk, SASS UBLKCP) signalled through an mbarrier.
+__device__ __forceinline__ void tma_bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* mbar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(mbar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(mbar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// Walk the anti-aliased ray of one horizon waypoint over a bit grid and record its free segments
+// (rp.py:466-520).  bits(row, word) returns the 32-bit word of the grid.
+template <typename Bits>
+__device__ __forceinline__ int walk_free_segments(const GridView& g, const double* bc, double min_width, short4* segs,
+                                                  int& bad, Bits&& bits) {
+    int ubx, uby, lbx, lby;
+    w2m(g, bc[0], bc[1], ubx, uby);  // rp.py:478
+    w2m(g, bc[2], bc[3], lbx, lby);  // rp.py:480
+    // every emitted cell lies within one pixel of the segment's bounding box
+    const bool inside = min(ubx, lbx) >= 1 && min(uby, lby) >= 1 && max(ubx, lbx) < g.W - 1 && max(uby, lby) < g.H - 1;
+    int uo_x = ubx, uo_y = uby, free_cells = 0, nseg = 0;
+    auto visit = [&](int x, int y) {
+        int xx = x, yy = y;
+        if (!inside) {  // numpy index semantics: negative wraps once, anything else is an IndexError
+            xx = x < 0 ? x + g.W : x; yy = y < 0 ? y + g.H : y;
+            if (xx < 0 || yy < 0 || xx >= g.W || yy >= g.H) { bad = 1; return; }
+        }
+        const int v = (bits(yy, xx >> 5) >> (xx & 31)) & 1u;
+        free_cells |= v;
+        const bool at_end = (x == lbx) & (y == lby);
+        if ((!v | at_end) & free_cells) {
+            double ux, uy, lx, ly;
+            m2w(g, uo_x, uo_y, ux, uy);
+            m2w(g, x, y, lx, ly);
+            if (sqrt(sq(ux - lx) + sq(uy - ly)) > min_width) {  // rp.py:510
+                if (nseg < kMaxSeg) segs[nseg] = make_short4((short)uo_x, (short)uo_y, (short)x, (short)y);
+                ++nseg;
+            }
+            uo_x = x; uo_y = y;
+            free_cells = 0;
+        } else if (!v) {  // occupied and no free run open (rp.py:516-518)
+            uo_x = x; uo_y = y;
+        }
+    };
+    // skimage.draw.line_aa(x0, y0, x1, y1): r = x, c = y; the first emitted cell is skipped (rp.py:494, Q4)
+    const int r0 = ubx, c0 = uby, r1 = lbx, c1 = lby;
+    const int dc = abs(c0 - c1), dr = abs(r0 - r1);
+    float err = (float)(dc - dr);
+    const int sign_c = (c0 < c1) ? 1 : -1, sign_r = (r0 < r1) ? 1 : -1;
+    const float ed = (dc + dr == 0) ? 1.0f : (float)sqrt((double)(dc * dc + dr * dr));
+    const float fdc = (float)dc, fdr = (float)dr;
+    int c = c0, r = r0;
+    bool first = true;
+    for (;;) {
+        if (!first) visit(r, c);
+        first = false;
+        const float e0 = err;
+        const int c_prev = c;
+        if (2 * e0 >= -fdc) {
+            if (c == c1) break;
+            if (e0 + fdr < ed) visit(r + sign_r, c);
+            err -= fdr;
+            c += sign_c;
+        }
+        if (2 * e0 <= fdr) {
+            if (r == r1) break;
+            if (fdc - e0 < ed) visit(r, c_prev + sign_c);
+            err += fdc;
+            r += sign_r;
+        }
+    }
+    return nseg;
+}
+
+struct RaycastArgs {
+    const uint32_t* grids;
+    size_t grid_stride_words;  // 0: every scenario uses the same grid
+    GridView g;
+    PathView pv;
+    const int2* rowspan;
+    const int* wp_id;
+    int first_offset, N;
+    double min_width, sm;
+    double *ub_out, *lb_out, *cells_sm_out;
+    int* flags;
+    int B;
+    int stage_rows;  // rows of shared memory reserved per staging slab (0: read the grid from global memory)
+};
+
+// MODE 0: no staging (global / L1 reads).  MODE 1: one grid shared by all scenarios, staged once per CTA
+// (whole grid, one TMA bulk copy) and reused by all warps and all scenarios the CTA loops over.
+// MODE 2: per-scenario grids, each warp stages the row span of its own scenario.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+raycast_kernel(RaycastArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int b = blockIdx.x, lane = threadIdx.x;
-    if (b >= B) return;
-    const int fl = flags ? flags[b] : 0;
-    if (fl & (MPC_ST_DEAD | MPC_ST_FINISHED)) return;
-    // shared layout: [grid rows][segments: N * kMaxSeg * int4][nseg: N ints][cells: N*4 doubles][mbar]
-    uint32_t* srow = reinterpret_cast<uint32_t*>(smem_raw);
-    const int max_rows_words = STAGED ? g.H * g.pitch_words : 0;
-    short4* segs = reinterpret_cast<short4*>(smem_raw + (size_t)max_rows_words * 4);
+    const GridView& g = a.g;
+    const PathView& pv = a.pv;
+    const int N = a.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // shared layout: [mbarriers: 8 x u64][staging slabs][per-warp scratch: segs, prev_cells, nsegs]
+    uint64_t* mbars = reinterpret_cast<uint64_t*>(smem_raw);
+    uint32_t* stage = reinterpret_cast<uint32_t*>(smem_raw + 128);
+    const size_t slab_words = (size_t)a.stage_rows * g.pitch_words;
+    const size_t stage_bytes = MODE == 1 ? slab_words * 4 : (MODE == 2 ? slab_words * 4 * nwarps : 0);
+    const size_t scratch_per_warp = (size_t)N * kMaxSeg * sizeof(short4) + (size_t)N * 4 * sizeof(double) + (size_t)((N + 3) & ~3) * sizeof(int);
+    unsigned char* scratch = smem_raw + 128 + stage_bytes + warp * scratch_per_warp;
+    short4* segs = reinterpret_cast<short4*>(scratch);
     double* prev_cells = reinterpret_cast<double*>(segs + (size_t)N * kMaxSeg);
     int* nsegs = reinterpret_cast<int*>(prev_cells + (size_t)N * 4);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(nsegs + ((N + 1) & ~1));
+    uint32_t* srow = MODE == 2 ? stage + warp * slab_words : stage;
 
-    long first = (long)wp_id[b] + first_offset;
-    int status = 0;
-    if (!pv.circular && first + N - 1 >= pv.n_wp) status |= MPC_ST_END_OF_PATH;  // rp.py:367-369
-    const int first_w = (int)(first % pv.n_wp);
-    const uint32_t* gsrc = grids + (size_t)b * grid_stride_words;
-    int row0 = 0;
-    if (STAGED) {
-        const int2 rs = rowspan[first_w];
-        row0 = rs.x;
-        const uint32_t bytes = (uint32_t)(rs.y - rs.x + 1) * g.pitch_words * 4;
-        if (lane == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
-            asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(srow)),
-                "l"(gsrc + (size_t)row0 * g.pitch_words), "r"(bytes), "r"(smem_u32(mbar))
-                : "memory");
+    if (MODE == 1) {
+        if (threadIdx.x == 0) {
+            mbar_init(&mbars[0], 1);
+            tma_bulk_load(stage, a.grids, (uint32_t)(slab_words * 4), &mbars[0]);
+        }
+        __syncthreads();
+        mbar_wait(&mbars[0], 0);
+    } else if (MODE == 2) {
+        if (lane == 0) mbar_init(&mbars[warp], 1);
+        __syncwarp();
+    }
+    uint32_t phase = 0;
+    for (int b = blockIdx.x * nwarps + warp; b < a.B; b += gridDim.x * nwarps) {
+        const int fl = a.flags ? a.flags[b] : 0;
+        if (fl & (MPC_ST_DEAD | MPC_ST_FINISHED)) continue;
+        const long first = (long)a.wp_id[b] + a.first_offset;
+        int status = 0;
+        if (!pv.circular && first + N - 1 >= pv.n_wp) status |= MPC_ST_END_OF_PATH;  // rp.py:367-369
+        const int first_w = (int)(first % pv.n_wp);
+        const uint32_t* gsrc = a.grids + (size_t)b * a.grid_stride_words;
+        int row0 = 0;
+        if (MODE == 2) {
+            const int2 rs = a.rowspan[first_w];
+            row0 = rs.x;
+            __syncwarp();  // every lane is done reading the previous scenario's rows
+            if (lane == 0)
+                tma_bulk_load(srow, gsrc + (size_t)row0 * g.pitch_words, (uint32_t)(rs.y - rs.x + 1) * g.pitch_words * 4,
+                              &mbars[warp]);
+            mbar_wait(&mbars[warp], phase);
+            phase ^= 1;
+        }
+        // ---- phase 1: free segments per horizon waypoint (rp.py:466-520), one lane per waypoint ----
+        for (int n = lane; n < N; n += 32) {
+            const int k = (first_w + n) % pv.n_wp;
+            int bad = 0, nseg;
+            if (MODE == 0)
+                nseg = walk_free_segments(g, pv.border + 4 * k, a.min_width, segs + n * kMaxSeg, bad,
+                                          [&](int y, int w) { return __ldg(gsrc + (size_t)y * g.pitch_words + w); });
+            else
+                nseg = walk_free_segments(g, pv.border + 4 * k, a.min_width, segs + n * kMaxSeg, bad,
+                                          [&](int y, int w) { return srow[(y - row0) * g.pitch_words + w]; });
+            if (bad || nseg > kMaxSeg) status |= MPC_ST_INDEX_ERROR;
+            nsegs[n] = nseg;
         }
         __syncwarp();
-        // wait for the bulk copy (phase 0)
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(done)
-                : "r"(smem_u32(mbar))
-                : "memory");
+        if (nsegs[0] == 0) status |= MPC_ST_NO_SEGMENT;  // rp.py:547 max([]) -> ValueError
+        status = __reduce_or_sync(0xffffffffu, status);
+        if (status) {
+            if (lane == 0 && a.flags) atomicOr(&a.flags[b], status | MPC_ST_DEAD);
+            continue;
         }
-    }
-    // ---- phase 1: free segments per horizon waypoint (rp.py:466-520) ----
-    for (int n = lane; n < N; n += 32) {
-        const int k = (first_w + n) % pv.n_wp;
-        const double* bc = pv.border + 4 * k;
-        int ubx, uby, lbx, lby;
-        w2m(g, bc[0], bc[1], ubx, uby);  // rp.py:478
-        w2m(g, bc[2], bc[3], lbx, lby);  // rp.py:480
-        int uo_x = ubx, uo_y = uby, free_cells = 0, nseg = 0, first_cell = 1, bad = 0;
-        line_aa_walk(ubx, uby, lbx, lby, [&](int x, int y) {
-            if (first_cell) { first_cell = 0; return true; }  // rp.py:494 skips the first cell (quirk Q4)
-            int xx = x < 0 ? x + g.W : x, yy = y < 0 ? y + g.H : y;
-            if (xx < 0 || yy < 0 || xx >= g.W || yy >= g.H) { bad = 1; return false; }
-            uint32_t wd;
-            if (STAGED) wd = srow[(yy - row0) * g.pitch_words + (xx >> 5)];
-            else wd = gsrc[(size_t)yy * g.pitch_words + (xx >> 5)];
-            const int v = (wd >> (xx & 31)) & 1u;
-            if (v) free_cells = 1;
-            if ((!v || (x == lbx && y == lby)) && free_cells) {
-                double ux, uy, lx, ly;
-                m2w(g, uo_x, uo_y, ux, uy);
-                m2w(g, x, y, lx, ly);
-                if (sqrt(sq(ux - lx) + sq(uy - ly)) > min_width) {  // rp.py:510
-                    if (nseg < kMaxSeg) segs[n * kMaxSeg + nseg] = make_short4((short)uo_x, (short)uo_y, (short)x, (short)y);
-                    ++nseg;
+        double* ub_o = a.ub_out + (size_t)b * N;
+        double* lb_o = a.lb_out + (size_t)b * N;
+        double* cs_o = a.cells_sm_out ? a.cells_sm_out + (size_t)b * N * 4 : nullptr;
+        // ---- phase 2: waypoints whose pick does not depend on the previous one ----
+        for (int n = lane; n < N; n += 32) {
+            const int k = (first_w + n) % pv.n_wp;
+            const int nseg = nsegs[n];
+            if (n > 0 && nseg >= 2) continue;
+            double ubx, uby, lbx, lby;
+            if (nseg == 0) { ubx = pv.x[k]; uby = pv.y[k]; lbx = ubx; lby = uby; }  // rp.py:595
+            else {
+                int best = 0;
+                if (n == 0 && nseg > 1) {  // largest segment, first maximum (rp.py:545-548)
+                    double bl = -1.0;
+                    for (int i = 0; i < nseg; ++i) {
+                        const short4 s4 = segs[n * kMaxSeg + i];
+                        double ux, uy, lx, ly;
+                        m2w(g, s4.x, s4.y, ux, uy);
+                        m2w(g, s4.z, s4.w, lx, ly);
+                        const double l = sqrt(sq(ux - lx) + sq(uy - ly));
+                        if (l > bl) { bl = l; best = i; }
+                    }
                 }
-                uo_x = x; uo_y = y;
-                free_cells = 0;
-            } else if (!v && !free_cells) {
-                uo_x = x; uo_y = y;
+                const short4 s4 = segs[n * kMaxSeg + best];
+                m2w(g, s4.x, s4.y, ubx, uby);
+                m2w(g, s4.z, s4.w, lbx, lby);
             }
-            return true;
-        });
-        if (bad || nseg > kMaxSeg) status |= MPC_ST_INDEX_ERROR;
-        nsegs[n] = nseg;
-    }
-    __syncwarp();
-    if (nsegs[0] == 0 && lane == 0) status |= MPC_ST_NO_SEGMENT;  // rp.py:547 max([]) -> ValueError
-    status = __reduce_or_sync(0xffffffffu, status);
-    if (status) {
-        if (lane == 0 && flags) atomicOr(&flags[b], status | MPC_ST_DEAD);
-        return;
-    }
-    // ---- phase 2: waypoints whose pick does not depend on the previous one ----
-    for (int n = lane; n < N; n += 32) {
-        const int k = (first_w + n) % pv.n_wp;
-        const int nseg = nsegs[n];
-        if (n > 0 && nseg >= 2) continue;
-        double ubx, uby, lbx, lby;
-        if (nseg == 0) { ubx = pv.x[k]; uby = pv.y[k]; lbx = ubx; lby = uby; }  // rp.py:595
-        else {
-            int best = 0;
-            if (n == 0 && nseg > 1) {  // largest segment, first maximum (rp.py:545-548)
-                double bl = -1.0;
-                for (int i = 0; i < nseg; ++i) {
-                    const short4 s4 = segs[n * kMaxSeg + i];
-                    double ux, uy, lx, ly;
-                    m2w(g, s4.x, s4.y, ux, uy);
-                    m2w(g, s4.z, s4.w, lx, ly);
-                    const double l = sqrt(sq(ux - lx) + sq(uy - ly));
-                    if (l > bl) { bl = l; best = i; }
-                }
-            }
-            const short4 s4 = segs[n * kMaxSeg + best];
-            m2w(g, s4.x, s4.y, ubx, uby);
-            m2w(g, s4.z, s4.w, lbx, lby);
-        }
-        const RayOut o = finalize_wp(pv, k, ubx, uby, lbx, lby, sm);
-        ub_out[(size_t)b * N + n] = o.ub;
-        lb_out[(size_t)b * N + n] = o.lb;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) prev_cells[4 * n + i] = o.cells[i];
-        if (cells_sm_out)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) cells_sm_out[((size_t)b * N + n) * 4 + i] = o.cells_sm[i];
-    }
-    __syncwarp();
-    // ---- phase 3: multi-candidate waypoints, in order (rp.py:552-586) ----
-    for (int n = 1; n < N; ++n) {
-        const int nseg = nsegs[n];  // warp-uniform
-        if (nseg < 2) continue;
-        const int k = (first_w + n) % pv.n_wp, kp = (first_w + n - 1) % pv.n_wp;
-        const double ds = pv.ds_next[kp];  // wp_prev - wp (rp.py:558)
-        const double upx = prev_cells[4 * (n - 1) + 0] + ds * pv.cos_psi[kp];  // rp.py:559
-        const double upy = prev_cells[4 * (n - 1) + 1] + ds * pv.cos_psi[kp];  // rp.py:560 (quirk Q2)
-        const double lpx = prev_cells[4 * (n - 1) + 2] + ds * pv.sin_psi[kp];  // rp.py:561
-        const double lpy = prev_cells[4 * (n - 1) + 3] + ds * pv.sin_psi[kp];  // rp.py:562
-        double md = INFINITY, ubx = 0, uby = 0, lbx = 0, lby = 0;
-        if (lane < nseg) {
-            const short4 s4 = segs[n * kMaxSeg + lane];
-            m2w(g, s4.x, s4.y, ubx, uby);
-            m2w(g, s4.z, s4.w, lbx, lby);
-            const double d_ub = sqrt(sq(ubx - upx) + sq(uby - upy));  // rp.py:576
-            const double d_lb = sqrt(sq(lbx - lpx) + sq(lby - lpy));  // rp.py:577
-            md = (d_ub + d_lb) / 2;
-        }
-        double wmd = md;
-        int wl = lane;
-#pragma unroll
-        for (int s = 4; s > 0; s >>= 1) {  // kMaxSeg = 8 candidates live in lanes 0..7
-            const double o = __shfl_xor_sync(0xffffffffu, wmd, s);
-            const int ol = __shfl_xor_sync(0xffffffffu, wl, s);
-            if (o < wmd || (o == wmd && ol < wl)) { wmd = o; wl = ol; }  // list.index(min()) = first minimum
-        }
-        wl = __shfl_sync(0xffffffffu, wl, 0);
-        if (lane == wl) {
-            const RayOut o = finalize_wp(pv, k, ubx, uby, lbx, lby, sm);
-            ub_out[(size_t)b * N + n] = o.ub;
-            lb_out[(size_t)b * N + n] = o.lb;
+            const RayOut o = finalize_wp(pv, k, ubx, uby, lbx, lby, a.sm);
+            ub_o[n] = o.ub;
+            lb_o[n] = o.lb;
 #pragma unroll
             for (int i = 0; i < 4; ++i) prev_cells[4 * n + i] = o.cells[i];
-            if (cells_sm_out)
+            if (cs_o)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) cells_sm_out[((size_t)b * N + n) * 4 + i] = o.cells_sm[i];
+                for (int i = 0; i < 4; ++i) cs_o[n * 4 + i] = o.cells_sm[i];
+        }
+        __syncwarp();
+        // ---- phase 3: multi-candidate waypoints, in order (rp.py:552-586) ----
+        for (int n = 1; n < N; ++n) {
+            const int nseg = nsegs[n];  // warp-uniform
+            if (nseg < 2) continue;
+            const int k = (first_w + n) % pv.n_wp, kp = (first_w + n - 1) % pv.n_wp;
+            const double ds = pv.ds_next[kp];  // wp_prev - wp (rp.py:558)
+            const double upx = prev_cells[4 * (n - 1) + 0] + ds * pv.cos_psi[kp];  // rp.py:559
+            const double upy = prev_cells[4 * (n - 1) + 1] + ds * pv.cos_psi[kp];  // rp.py:560 (quirk Q2)
+            const double lpx = prev_cells[4 * (n - 1) + 2] + ds * pv.sin_psi[kp];  // rp.py:561
+            const double lpy = prev_cells[4 * (n - 1) + 3] + ds * pv.sin_psi[kp];  // rp.py:562
+            double md = INFINITY, ubx = 0, uby = 0, lbx = 0, lby = 0;
+            if (lane < nseg) {
+                const short4 s4 = segs[n * kMaxSeg + lane];
+                m2w(g, s4.x, s4.y, ubx, uby);
+                m2w(g, s4.z, s4.w, lbx, lby);
+                const double d_ub = sqrt(sq(ubx - upx) + sq(uby - upy));  // rp.py:576
+                const double d_lb = sqrt(sq(lbx - lpx) + sq(lby - lpy));  // rp.py:577
+                md = (d_ub + d_lb) / 2;
+            }
+            double wmd = md;
+            int wl = lane;
+#pragma unroll
+            for (int s = 4; s > 0; s >>= 1) {  // kMaxSeg = 8 candidates live in lanes 0..7
+                const double o = __shfl_xor_sync(0xffffffffu, wmd, s);
+                const int ol = __shfl_xor_sync(0xffffffffu, wl, s);
+                if (o < wmd || (o == wmd && ol < wl)) { wmd = o; wl = ol; }  // list.index(min()) = first minimum
+            }
+            wl = __shfl_sync(0xffffffffu, wl, 0);
+            if (lane == wl) {
+                const RayOut o = finalize_wp(pv, k, ubx, uby, lbx, lby, a.sm);
+                ub_o[n] = o.ub;
+                lb_o[n] = o.lb;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) prev_cells[4 * n + i] = o.cells[i];
+                if (cs_o)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) cs_o[n * 4 + i] = o.cells_sm[i];
+            }
+            __syncwarp();
         }
         __syncwarp();
     }
 }
 
-size_t raycast_smem_bytes(const GridView& g, int N, bool staged) {
-    size_t s = staged ? (size_t)g.H * g.pitch_words * 4 : 0;
-    s += (size_t)N * kMaxSeg * sizeof(short4) + (size_t)N * 4 * sizeof(double) + (size_t)((N + 1) & ~1) * sizeof(int) + 16;
+static size_t raycast_scratch_bytes(int N) {
+    return (size_t)N * kMaxSeg * sizeof(short4) + (size_t)N * 4 * sizeof(double) + (size_t)((N + 3) & ~3) * sizeof(int);
+}
+
+// shared-memory bytes of one CTA for the given mode (stage_rows rows per slab)
+size_t raycast_smem_bytes(const GridView& g, int N, int mode, int stage_rows, int warps) {
+    size_t s = 128 + (size_t)warps * raycast_scratch_bytes(N);
+    if (mode == 1) s += (size_t)stage_rows * g.pitch_words * 4;
+    if (mode == 2) s += (size_t)warps * stage_rows * g.pitch_words * 4;
     return s;
 }
 
+// mode selection: 1 (shared grid, whole grid in shared memory) / 2 (per-scenario grids, row span per warp) when they
+// fit, otherwise 0 (global reads).  Returns the launch geometry through the out parameters.
+int raycast_plan(const GridView& g, int N, bool shared_grid, int max_rows, bool rowspan_ok, int* warps, int* stage_rows,
+                 size_t* smem) {
+    const size_t kLimit = 200 * 1024;
+    if (shared_grid) {
+        *warps = 8; *stage_rows = g.H;
+        *smem = raycast_smem_bytes(g, N, 1, g.H, 8);
+        if (*smem <= kLimit / 2) return 1;
+    } else if (rowspan_ok) {
+        for (int w = 4; w >= 1; w >>= 1) {
+            *warps = w; *stage_rows = max_rows;
+            *smem = raycast_smem_bytes(g, N, 2, max_rows, w);
+            if (*smem <= kLimit / 2 || (w == 1 && *smem <= kLimit)) return 2;
+        }
+    }
+    *warps = 8; *stage_rows = 0;
+    *smem = raycast_smem_bytes(g, N, 0, 0, 8);
+    return 0;
+}
+
 void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridView& g, const PathView& pv,
-                    const int2* rowspan, const int* wp_id, int first_offset, int N, double min_width, double sm,
-                    double* ub, double* lb, double* cells_sm, int* flags, int B, bool staged, cudaStream_t st) {
-    const size_t smem = raycast_smem_bytes(g, N, staged);
-    if (staged) {
-        cudaFuncSetAttribute(raycast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        raycast_kernel<true><<<B, 32, smem, st>>>(grids, grid_stride_words, g, pv, rowspan, wp_id, first_offset, N,
-                                                  min_width, sm, ub, lb, cells_sm, flags, B);
+                    const int2* rowspan, int max_rows, const int* wp_id, int first_offset, int N, double min_width,
+                    double sm, double* ub, double* lb, double* cells_sm, int* flags, int B, bool rowspan_ok,
+                    cudaStream_t st) {
+    RaycastArgs a;
+    a.grids = grids; a.grid_stride_words = grid_stride_words; a.g = g; a.pv = pv; a.rowspan = rowspan; a.wp_id = wp_id;
+    a.first_offset = first_offset; a.N = N; a.min_width = min_width; a.sm = sm; a.ub_out = ub; a.lb_out = lb;
+    a.cells_sm_out = cells_sm; a.flags = flags; a.B = B;
+    int warps = 8, stage_rows = 0;
+    size_t smem = 0;
+    const int mode = raycast_plan(g, N, grid_stride_words == 0, max_rows, rowspan_ok, &warps, &stage_rows, &smem);
+    a.stage_rows = stage_rows;
+    const int ctas_needed = (B + warps - 1) / warps;
+    // persistent-style grid: enough CTAs to fill the machine a few times over, each looping over scenarios
+    const int max_ctas = 148 * 8;
+    const int grid = ctas_needed < max_ctas ? ctas_needed : max_ctas;
+    if (mode == 1) {
+        cudaFuncSetAttribute(raycast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        raycast_kernel<1><<<grid, warps * 32, smem, st>>>(a);
+    } else if (mode == 2) {
+        cudaFuncSetAttribute(raycast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        raycast_kernel<2><<<grid, warps * 32, smem, st>>>(a);
     } else {
-        cudaFuncSetAttribute(raycast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        raycast_kernel<false><<<B, 32, smem, st>>>(grids, grid_stride_words, g, pv, rowspan, wp_id, first_offset, N,
-                                                   min_width, sm, ub, lb, cells_sm, flags, B);
+        cudaFuncSetAttribute(raycast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        raycast_kernel<0><<<grid, warps * 32, smem, st>>>(a);
     }
 }
 

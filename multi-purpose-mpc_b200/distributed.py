@@ -48,14 +48,16 @@ def max_over_ranks(value, device=None):
     return float(t.item())
 
 
-def make_scenarios(track_n_wp, B, seed, kind="tracking", wp_xy_psi=None):
+def make_scenarios(track_n_wp, B, seed, kind="tracking", wp_xy_psi=None, max_start_wp=None):
     """Synthetic scenario generator of SURVEY.md section 8d (same on every rank: generate all B, then slice).
     kind = "tracking": C2 -- start waypoint U{0..n_wp-1}, e_y ~ U(-0.05, 0.05), e_psi ~ U(-0.1, 0.1).
     kind = "obstacles": C3 -- additionally K ~ U{4..12} discs per scenario at random waypoints with lateral
     offset U(-0.15, 0.15) m and radius U(0.04, 0.08) m, rejected within 0.3 m of the start pose.
     Returns dict(start_wp, e_y, e_psi[, obs (n,3), obs_off (B+1,)])."""
     rng = np.random.default_rng(seed)
-    out = dict(start_wp=rng.integers(0, track_n_wp, B), e_y=rng.uniform(-0.05, 0.05, B),
+    # benchmarks keep the start waypoints away from the finish line so that no car ends its lap mid-run
+    hi_wp = track_n_wp if max_start_wp is None else int(max_start_wp)
+    out = dict(start_wp=rng.integers(0, hi_wp, B), e_y=rng.uniform(-0.05, 0.05, B),
                e_psi=rng.uniform(-0.1, 0.1, B))
     if kind == "obstacles":
         assert wp_xy_psi is not None

@@ -18,7 +18,7 @@ def sim(track, tmp_path_factory):
     from mpc_b200.spatial_bicycle_models import BicycleModel
     from mpc_b200.MPC import MPC
     # an image whose channel 0 binarises (>= 100) to the reference's sim_map grid
-    img = np.repeat((track.grid * 255).astype(np.uint8)[:, :, None], 3, axis=2)
+    img = np.repeat((track.grid.astype(np.uint8) * 255)[:, :, None], 3, axis=2)
     p = tmp_path_factory.mktemp("maps") / "sim_map.png"
     Image.fromarray(img).save(p)
     mp = Map(file_path=str(p), origin=[-1, -2], resolution=0.005)

@@ -47,9 +47,9 @@ def test_qp_matches_oracle(orc, precision, eps):
     eng.close()
     assert np.array_equal(st, sto), "status differs from the oracle"
     assert np.array_equal(it, ito), "iteration counts differ from the oracle"
-    ok = sto > 0
+    ok = ~np.isin(sto, (-3, -4, -7))                    # OSQP returns an iterate (also for max-iter, -2)
     assert ok.sum() >= 60 and (~ok).sum() >= 6          # the fixture contains infeasible QPs too
-    assert np.isnan(x[~ok]).all()                        # OSQP returns no solution there (MPC.py:208)
+    assert np.isnan(x[~ok]).all() and np.isnan(xo[~ok]).all()   # no solution there (MPC.py:208 path)
     d = np.abs(x[ok] - xo[ok]).max(axis=1)
     assert d.max() <= (QP_TOL if precision == 0 else 1e-4), d.max()
 
@@ -154,22 +154,31 @@ def test_raycast_no_free_segment_is_flagged(engine_factory, track):
     assert int(fl[0].item()) & mpc_b200.ST_NO_SEGMENT
 
 
-def test_staged_and_direct_raycast_agree(engine_factory, track):
-    """TMA-staged rows (horizon N = engine N) and the direct global-memory walk (other N) give the same bits."""
+def test_raycast_modes_agree(engine_factory, track):
+    """The three grid-access modes of K3 give the same bits: whole shared grid staged once per CTA by TMA
+    (mode 1), per-scenario row span staged per warp by TMA (mode 2), direct global-memory walk (mode 0)."""
     import torch
-    eng = engine_factory()
     sm = 0.06 / np.sqrt(2)
     wid = _t(np.arange(0, 200, 7), torch.int32)
     B = wid.shape[0]
-    out = {}
-    for N in (30, 29):
+
+    def run(eng, N):
         ub = torch.zeros((B, N), dtype=torch.float64, device=_dev())
         lb = torch.zeros_like(ub)
         fl = torch.zeros(B, dtype=torch.int32, device=_dev())
         eng.update_path_constraints(wid, 1, N, 2 * sm, sm, ub, lb, None, fl)
         eng.sync()
-        out[N] = (ub.cpu().numpy(), lb.cpu().numpy())
-    assert np.array_equal(out[30][0][:, :29], out[29][0]) and np.array_equal(out[30][1][:, :29], out[29][1])
+        assert int(fl.sum().item()) == 0
+        return ub.cpu().numpy(), lb.cpu().numpy()
+
+    shared = engine_factory(grid="obstacles")                      # mode 1
+    per = engine_factory(grid="free")                              # per-scenario copies of the same nine discs
+    per.set_obstacles(np.tile(track.obstacles, (B, 1)), np.arange(B + 1, dtype=np.int32) * len(track.obstacles))
+    u1, l1 = run(shared, 30)
+    u2, l2 = run(per, 30)                                          # mode 2 (row span table is for N = 30)
+    u0, l0 = run(per, 29)                                          # mode 0 (no row span table for N = 29)
+    assert np.array_equal(u1, u2) and np.array_equal(l1, l2)
+    assert np.array_equal(u1[:, :29], u0) and np.array_equal(l1[:, :29], l0)
 
 
 # ------------------------------------------------------------------ full step, teacher forced -------
@@ -277,8 +286,10 @@ def test_batch_properties_at_c2_size(engine_factory, track):
         assert np.array_equal(o1[k][:, perm], o2[k])
     for k in ("u", "iters", "qp_status", "wp_id", "ub", "lb"):
         assert np.array_equal(o1[k][perm], o2[k]), k
-    assert (o1["qp_status"] == 1).mean() > 0.9
-    assert (o1["u"][:, 0] > 0).all() and (np.abs(o1["u"][:, 1]) <= 0.66 + 1e-6).all()
+    solved = o1["qp_status"] == 1
+    assert solved.mean() > 0.9, solved.mean()
+    # an eps = 1e-3 ADMM iterate may sit a hair outside the box; the bounds hold to the solver tolerance
+    assert o1["u"][solved, 0].min() > -5e-3 and np.abs(o1["u"][solved, 1]).max() <= 0.66 + 5e-3
 
 
 def test_speed_profile_matches_reference(track):
