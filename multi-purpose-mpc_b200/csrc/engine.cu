@@ -489,6 +489,8 @@ int mpc_scenarios_set_state(mpc_engine* h, const double* h_state, const double* 
     CUDA_OK(cudaMemsetAsync(h->s_wp_id.p, 0, (size_t)B * sizeof(int), s));
     CUDA_OK(cudaMemsetAsync(h->s_spatial.p, 0, 2 * (size_t)B * sizeof(double), s));
     CUDA_OK(cudaMemsetAsync(h->s_u.p, 0, 2 * (size_t)B * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(h->s_ub.p, 0, (size_t)N * B * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(h->s_lb.p, 0, (size_t)N * B * sizeof(double), s));
     CUDA_OK(cudaStreamSynchronize(s));
     return 0;
 }

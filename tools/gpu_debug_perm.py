@@ -28,3 +28,8 @@ for prec in (0, 1):
     bad = np.nonzero(np.any((o1["u"][perm] != o2["u"]).reshape(B, -1), axis=1))[0][:5]
     for i in bad:
         print("  row", i, "orig idx", perm[i], o1["u"][perm][i], o2["u"][i], o1["iters"][perm][i], o2["iters"][i], o1["flags"][perm][i], o2["flags"][i], "wp", o2["wp_id"][i])
+o = run(st, 0)
+import collections
+print("status hist", collections.Counter(o["qp_status"].tolist()), "flags", collections.Counter(o["flags"].tolist()))
+s1 = o["qp_status"] == 1
+print("u0 min", o["u"][s1, 0].min(), "max |delta|", np.abs(o["u"][s1, 1]).max(), "iters mean", o["iters"].mean())
