@@ -7,16 +7,68 @@
 namespace mpcb {
 
 constexpr int kWarpsPerBlock = 2;
+
 // Tuning point per precision: RLEV = PCR levels kept in registers (the rest in shared memory),
 // MINB = minimum resident blocks per SM handed to __launch_bounds__ (caps registers per thread).
 template <typename T> struct Tune;
 template <> struct Tune<float> { static constexpr int rlev = 5, minb = 4; };
 template <> struct Tune<double> { static constexpr int rlev = 0, minb = 4; };
 template <int NLEV, int RLEV> constexpr int clamp_rlev() { return RLEV < NLEV ? RLEV : NLEV; }
-template <typename T, int NLEV, int RLEV> constexpr size_t smem_bytes() {
-    return (size_t)kWarpsPerBlock * (kConstRows + 18 * (NLEV - RLEV)) * 32 * sizeof(T);
+template <typename T, int NLEV, int RLEV> constexpr size_t warp_smem_bytes() {
+    return (size_t)kWarpsPerBlock * smem_rows<NLEV, RLEV>() * 32 * sizeof(T);
+}
+// block-per-scenario kernels (N + 1 > 32): [comm slots (8 B each)][const rows + factor rows][NT]
+template <typename T, int NLEV, int NT> constexpr size_t block_smem_bytes() {
+    return (size_t)BlockComm<NT>::slots() * 8 + (size_t)smem_rows<NLEV, 0>() * NT * sizeof(T);
 }
 
+// what the reference does with dec.x (MPC.py:185-220): new plan + first control, or replay of the previous plan
+template <typename T>
+__device__ __forceinline__ void write_solution(int N, int lane, const T w[5], double* xo) {
+    if (!xo || lane > N) return;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) xo[3 * lane + i] = (double)w[i];
+    if (lane < N) { xo[3 * (N + 1) + 2 * lane] = (double)w[3]; xo[3 * (N + 1) + 2 * lane + 1] = (double)w[4]; }
+}
+
+template <typename T, typename Comm>
+__device__ __forceinline__ void control_epilogue(Comm& cm, const MpcParams& mp, int lane, const T w[5], const SolveResult& r,
+                                                 double* cc, int* infeas, double* u_out, int* iters, int* qp_status,
+                                                 int* flags, int b, int fl) {
+    const int N = mp.N;
+    const bool ok = !(r.status == -3 || r.status == -4 || r.status == -7);  // OSQP returns x (MPC.py:185-206)
+    int inf = infeas[b];
+    cm.sync();
+    if (ok) {
+        if (lane < N) {
+            cc[2 * lane] = (double)w[3];                   // MPC.py:187
+            cc[2 * lane + 1] = atan((double)w[4] * mp.L);  // MPC.py:188-189
+        }
+        if (lane == 0) {
+            u_out[2 * (size_t)b] = (double)w[3];
+            u_out[2 * (size_t)b + 1] = atan((double)w[4] * mp.L);
+            inf = 0;  // MPC.py:206
+            fl &= ~MPC_ST_QP_FALLBACK;
+        }
+    } else if (lane == 0) {
+        const int id = 2 * (inf + 1);  // MPC.py:212-213
+        u_out[2 * (size_t)b] = cc[id];
+        u_out[2 * (size_t)b + 1] = cc[id + 1];
+        inf += 1;  // MPC.py:216
+        fl |= MPC_ST_QP_FALLBACK;
+    }
+    if (lane == 0) {
+        if (inf == N - 1) fl |= MPC_ST_DEAD;  // MPC.py:218-220
+        infeas[b] = inf;
+        if (flags) flags[b] = fl;
+        if (iters) iters[b] = r.iters;
+        if (qp_status) qp_status[b] = r.status;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp-per-scenario kernels (N + 1 <= 32)
+// ------------------------------------------------------------------------------------------------
 template <typename T, int NLEV, int RLEV, int MINB>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, MINB)
 solve_qp_kernel(int N, AdmmSettings st, const double* __restrict__ Pd, const double* __restrict__ q,
@@ -29,16 +81,12 @@ solve_qp_kernel(int N, AdmmSettings st, const double* __restrict__ Pd, const dou
     Stage<T> s;
     load_stage_qp<T>(s, N, lane, Pd + (size_t)b * n, q + (size_t)b * n, Ax + (size_t)b * nnz, l + (size_t)b * m,
                      u + (size_t)b * m);
-    T w[5];
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* sm = reinterpret_cast<T*>(smem_raw) + (size_t)(threadIdx.x >> 5) * smem_rows_per_warp<NLEV, RLEV>() * 32;
-    const SolveResult r = admm_solve<T, NLEV, RLEV>(s, st, lane, N + 1, n, sm, w);
-    if (x_out && lane <= N) {
-        double* xo = x_out + (size_t)b * n;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) xo[3 * lane + i] = (double)w[i];
-        if (lane < N) { xo[3 * (N + 1) + 2 * lane] = (double)w[3]; xo[3 * (N + 1) + 2 * lane + 1] = (double)w[4]; }
-    }
+    T* sm = reinterpret_cast<T*>(smem_raw) + (size_t)(threadIdx.x >> 5) * smem_rows<NLEV, RLEV>() * 32;
+    WarpComm cm(nullptr);
+    T w[5];
+    const SolveResult r = admm_solve<T, NLEV, RLEV>(cm, s, st, lane, N + 1, n, sm, w);
+    write_solution<T>(N, lane, w, x_out ? x_out + (size_t)b * n : nullptr);
     if (lane == 0) {
         if (iters) iters[b] = r.iters;
         if (status) status[b] = r.status;
@@ -55,60 +103,83 @@ assemble_solve_kernel(MpcParams mp, AdmmSettings st, PathView pv, const double* 
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (b >= B) return;
-    int fl = flags ? flags[b] : 0;
+    const int fl = flags ? flags[b] : 0;
     if (fl & (MPC_ST_DEAD | MPC_ST_FINISHED)) return;
     const int N = mp.N, n = 5 * N + 3;
     double* cc = control + (size_t)b * 2 * N;
     Stage<T> s;
     assemble_stage<T>(s, mp, pv, lane, wp_id[b], spatial[b], spatial[(size_t)B + b], cc, ub + (size_t)b * N,
                       lb + (size_t)b * N);
-    T w[5];
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* sm = reinterpret_cast<T*>(smem_raw) + (size_t)(threadIdx.x >> 5) * smem_rows_per_warp<NLEV, RLEV>() * 32;
-    const SolveResult r = admm_solve<T, NLEV, RLEV>(s, st, lane, N + 1, n, sm, w);
-    const bool ok = !(r.status == -3 || r.status == -4 || r.status == -7);  // OSQP returns x (MPC.py:185-206)
-    if (x_out && lane <= N) {
-        double* xo = x_out + (size_t)b * n;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) xo[3 * lane + i] = (double)w[i];
-        if (lane < N) { xo[3 * (N + 1) + 2 * lane] = (double)w[3]; xo[3 * (N + 1) + 2 * lane + 1] = (double)w[4]; }
-    }
-    int inf = infeas[b];
-    __syncwarp();
-    if (ok) {
-        if (lane < N) {
-            cc[2 * lane] = (double)w[3];                         // MPC.py:187
-            cc[2 * lane + 1] = atan((double)w[4] * mp.L);        // MPC.py:188-189
-        }
-        if (lane == 0) {
-            u_out[2 * (size_t)b] = (double)w[3];
-            u_out[2 * (size_t)b + 1] = atan((double)w[4] * mp.L);
-            inf = 0;                                             // MPC.py:206
-            fl &= ~MPC_ST_QP_FALLBACK;
-        }
-    } else if (lane == 0) {
-        const int id = 2 * (inf + 1);                            // MPC.py:212-213
-        u_out[2 * (size_t)b] = cc[id];
-        u_out[2 * (size_t)b + 1] = cc[id + 1];
-        inf += 1;                                                // MPC.py:216
-        fl |= MPC_ST_QP_FALLBACK;
-    }
+    T* sm = reinterpret_cast<T*>(smem_raw) + (size_t)(threadIdx.x >> 5) * smem_rows<NLEV, RLEV>() * 32;
+    WarpComm cm(nullptr);
+    T w[5];
+    const SolveResult r = admm_solve<T, NLEV, RLEV>(cm, s, st, lane, N + 1, n, sm, w);
+    write_solution<T>(N, lane, w, x_out ? x_out + (size_t)b * n : nullptr);
+    control_epilogue<T>(cm, mp, lane, w, r, cc, infeas, u_out, iters, qp_status, flags, b, fl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-per-scenario kernels (32 < N + 1 <= NT): one thread per stage, shared-memory exchange
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NLEV, int NT>
+__global__ void __launch_bounds__(NT, 1)
+solve_qp_block_kernel(int N, AdmmSettings st, const double* __restrict__ Pd, const double* __restrict__ q,
+                      const double* __restrict__ Ax, const double* __restrict__ l, const double* __restrict__ u,
+                      double* __restrict__ x_out, int* __restrict__ iters, int* __restrict__ status, int B) {
+    const int lane = threadIdx.x, b = blockIdx.x;
+    if (b >= B) return;
+    const int n = 5 * N + 3, m = 8 * N + 6, nnz = 16 * N + 6;
+    Stage<T> s;
+    load_stage_qp<T>(s, N, lane, Pd + (size_t)b * n, q + (size_t)b * n, Ax + (size_t)b * nnz, l + (size_t)b * m,
+                     u + (size_t)b * m);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BlockComm<NT> cm(smem_raw);
+    T* sm = reinterpret_cast<T*>(smem_raw + (size_t)BlockComm<NT>::slots() * 8);
+    T w[5];
+    const SolveResult r = admm_solve<T, NLEV, 0>(cm, s, st, lane, N + 1, n, sm, w);
+    write_solution<T>(N, lane, w, x_out ? x_out + (size_t)b * n : nullptr);
     if (lane == 0) {
-        if (inf == N - 1) fl |= MPC_ST_DEAD;                     // MPC.py:218-220
-        infeas[b] = inf;
-        if (flags) flags[b] = fl;
         if (iters) iters[b] = r.iters;
-        if (qp_status) qp_status[b] = r.status;
+        if (status) status[b] = r.status;
     }
 }
 
+template <typename T, int NLEV, int NT>
+__global__ void __launch_bounds__(NT, 1)
+assemble_solve_block_kernel(MpcParams mp, AdmmSettings st, PathView pv, const double* __restrict__ spatial,
+                            const int* __restrict__ wp_id, double* __restrict__ control, const double* __restrict__ ub,
+                            const double* __restrict__ lb, int* __restrict__ infeas, double* __restrict__ u_out,
+                            double* __restrict__ x_out, int* __restrict__ iters, int* __restrict__ qp_status,
+                            int* __restrict__ flags, int B) {
+    const int lane = threadIdx.x, b = blockIdx.x;
+    if (b >= B) return;
+    const int fl = flags ? flags[b] : 0;
+    if (fl & (MPC_ST_DEAD | MPC_ST_FINISHED)) return;
+    const int N = mp.N, n = 5 * N + 3;
+    double* cc = control + (size_t)b * 2 * N;
+    Stage<T> s;
+    assemble_stage<T>(s, mp, pv, lane, wp_id[b], spatial[b], spatial[(size_t)B + b], cc, ub + (size_t)b * N,
+                      lb + (size_t)b * N);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BlockComm<NT> cm(smem_raw);
+    T* sm = reinterpret_cast<T*>(smem_raw + (size_t)BlockComm<NT>::slots() * 8);
+    T w[5];
+    const SolveResult r = admm_solve<T, NLEV, 0>(cm, s, st, lane, N + 1, n, sm, w);
+    write_solution<T>(N, lane, w, x_out ? x_out + (size_t)b * n : nullptr);
+    control_epilogue<T>(cm, mp, lane, w, r, cc, infeas, u_out, iters, qp_status, flags, b, fl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
 template <typename T, int NLEV, int RLEV, int MINB>
 static void solve_qp_launch(int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax,
                             const double* l, const double* u, double* x_out, int* iters, int* status, int B,
                             cudaStream_t s) {
     constexpr int R = clamp_rlev<NLEV, RLEV>();
     const int grid = (B + kWarpsPerBlock - 1) / kWarpsPerBlock, block = 32 * kWarpsPerBlock;
-    const size_t smem = smem_bytes<T, NLEV, R>();
+    const size_t smem = warp_smem_bytes<T, NLEV, R>();
     cudaFuncSetAttribute(solve_qp_kernel<T, NLEV, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     solve_qp_kernel<T, NLEV, R, MINB><<<grid, block, smem, s>>>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B);
 }
@@ -120,41 +191,47 @@ static void assemble_solve_launch(const MpcParams& mp, const AdmmSettings& st, c
                                   cudaStream_t s) {
     constexpr int R = clamp_rlev<NLEV, RLEV>();
     const int grid = (B + kWarpsPerBlock - 1) / kWarpsPerBlock, block = 32 * kWarpsPerBlock;
-    const size_t smem = smem_bytes<T, NLEV, R>();
+    const size_t smem = warp_smem_bytes<T, NLEV, R>();
     cudaFuncSetAttribute(assemble_solve_kernel<T, NLEV, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     assemble_solve_kernel<T, NLEV, R, MINB><<<grid, block, smem, s>>>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas,
                                                                       u_out, x_out, iters, qp_status, flags, B);
 }
 
-#ifdef MPC_TUNING_VARIANTS
-// development only: extra fp32 instantiations of the QP-only kernel selected with MPC_TUNE="rlev,minb"
-static bool tuned_solve_qp(int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax,
-                           const double* l, const double* u, double* x_out, int* iters, int* status, int B,
-                           cudaStream_t s) {
-    const char* e = getenv("MPC_TUNE");
-    if (!e || N + 1 <= 16) return false;
-    int r = 5, m = 4;
-    sscanf(e, "%d,%d", &r, &m);
-#define V(R_, M_) if (r == R_ && m == M_) { solve_qp_launch<float, 5, R_, M_>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s); return true; }
-    V(5, 5) V(5, 6) V(3, 6) V(3, 8) V(2, 8) V(0, 8) V(0, 10)
-#undef V
-    return false;
+template <typename T, int NLEV, int NT>
+static void solve_qp_block_launch(int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax,
+                                  const double* l, const double* u, double* x_out, int* iters, int* status, int B,
+                                  cudaStream_t s) {
+    const size_t smem = block_smem_bytes<T, NLEV, NT>();
+    cudaFuncSetAttribute(solve_qp_block_kernel<T, NLEV, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    solve_qp_block_kernel<T, NLEV, NT><<<B, NT, smem, s>>>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B);
 }
-#endif
+
+template <typename T, int NLEV, int NT>
+static void assemble_solve_block_launch(const MpcParams& mp, const AdmmSettings& st, const PathView& pv,
+                                        const double* spatial, const int* wp_id, double* control, const double* ub,
+                                        const double* lb, int* infeas, double* u_out, double* x_out, int* iters,
+                                        int* qp_status, int* flags, int B, cudaStream_t s) {
+    const size_t smem = block_smem_bytes<T, NLEV, NT>();
+    cudaFuncSetAttribute(assemble_solve_block_kernel<T, NLEV, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    assemble_solve_block_kernel<T, NLEV, NT><<<B, NT, smem, s>>>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out,
+                                                                x_out, iters, qp_status, flags, B);
+}
 
 int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax,
                     const double* l, const double* u, double* x_out, int* iters, int* status, int B, cudaStream_t s) {
-    if (N + 1 > 32) return MPC_E_UNSUPPORTED;
+#define WARP_GO(T_, L_) solve_qp_launch<T_, L_, Tune<T_>::rlev, Tune<T_>::minb>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s)
+#define BLOCK_GO(T_, L_, NT_) solve_qp_block_launch<T_, L_, NT_>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s)
+    const int ns = N + 1;
+    if (ns > 128) return MPC_E_UNSUPPORTED;
     if (precision == 1) {
-        if (N + 1 <= 16) solve_qp_launch<double, 4, Tune<double>::rlev, Tune<double>::minb>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s);
-        else solve_qp_launch<double, 5, Tune<double>::rlev, Tune<double>::minb>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s);
-        return 0;
+        if (ns <= 16) WARP_GO(double, 4); else if (ns <= 32) WARP_GO(double, 5);
+        else if (ns <= 64) BLOCK_GO(double, 6, 64); else BLOCK_GO(double, 7, 128);
+    } else {
+        if (ns <= 16) WARP_GO(float, 4); else if (ns <= 32) WARP_GO(float, 5);
+        else if (ns <= 64) BLOCK_GO(float, 6, 64); else BLOCK_GO(float, 7, 128);
     }
-#ifdef MPC_TUNING_VARIANTS
-    if (tuned_solve_qp(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s)) return 0;
-#endif
-    if (N + 1 <= 16) solve_qp_launch<float, 4, Tune<float>::rlev, Tune<float>::minb>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s);
-    else solve_qp_launch<float, 5, Tune<float>::rlev, Tune<float>::minb>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s);
+#undef WARP_GO
+#undef BLOCK_GO
     return 0;
 }
 
@@ -162,11 +239,19 @@ int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings
                           const double* spatial, const int* wp_id, double* control, const double* ub, const double* lb,
                           int* infeas, double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
                           cudaStream_t s) {
-    if (mp.N + 1 > 32) return MPC_E_UNSUPPORTED;
-#define GO(T_, L_) assemble_solve_launch<T_, L_, Tune<T_>::rlev, Tune<T_>::minb>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s)
-    if (precision == 1) { if (mp.N + 1 <= 16) GO(double, 4); else GO(double, 5); }
-    else { if (mp.N + 1 <= 16) GO(float, 4); else GO(float, 5); }
-#undef GO
+#define WARP_GO(T_, L_) assemble_solve_launch<T_, L_, Tune<T_>::rlev, Tune<T_>::minb>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s)
+#define BLOCK_GO(T_, L_, NT_) assemble_solve_block_launch<T_, L_, NT_>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s)
+    const int ns = mp.N + 1;
+    if (ns > 128) return MPC_E_UNSUPPORTED;
+    if (precision == 1) {
+        if (ns <= 16) WARP_GO(double, 4); else if (ns <= 32) WARP_GO(double, 5);
+        else if (ns <= 64) BLOCK_GO(double, 6, 64); else BLOCK_GO(double, 7, 128);
+    } else {
+        if (ns <= 16) WARP_GO(float, 4); else if (ns <= 32) WARP_GO(float, 5);
+        else if (ns <= 64) BLOCK_GO(float, 6, 64); else BLOCK_GO(float, 7, 128);
+    }
+#undef WARP_GO
+#undef BLOCK_GO
     return 0;
 }
 

@@ -50,29 +50,83 @@ struct PathView {  // device tables, one row per quantity (set by mpc_set_path)
 };
 
 // ------------------------------------------------------------------------------------------------
-// warp helpers
+// neighbour exchange + reductions between the stages of one scenario
 // ------------------------------------------------------------------------------------------------
-template <typename T> __device__ __forceinline__ T shfl_up(T v, int s) { return __shfl_up_sync(kFull, v, s); }
-template <typename T> __device__ __forceinline__ T shfl_dn(T v, int s) { return __shfl_down_sync(kFull, v, s); }
+// WarpComm : one warp per scenario, stage = lane (N + 1 <= 32): shuffles and redux.sync.
+// BlockComm: one CTA of NT threads per scenario, stage = thread (N + 1 <= NT <= 128): double-buffered
+//            shared-memory exchange, one __syncthreads per exchange.  Same math, longer horizons.
+struct WarpComm {
+    static constexpr int W = 32;
+    __device__ __forceinline__ explicit WarpComm(void*) {}
+    __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+    template <typename T> __device__ __forceinline__ T up(T v, int s) { return __shfl_up_sync(kFull, v, s); }
+    template <typename T> __device__ __forceinline__ T dn(T v, int s) { return __shfl_down_sync(kFull, v, s); }
+    __device__ __forceinline__ float max(float v) {  // v >= 0: order of the bit pattern = order of the value
+        return __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(v)));
+    }
+    __device__ __forceinline__ double max(double v) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, s));
+        return v;
+    }
+    template <typename T> __device__ __forceinline__ T sum(T v) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(kFull, v, s);
+        return v;
+    }
+    __device__ __forceinline__ bool any(bool p) { return __any_sync(kFull, p); }
+    __device__ __forceinline__ void sync() { __syncwarp(); }
+};
 
-__device__ __forceinline__ float warp_max(float v) {  // v >= 0: order of the bit pattern = order of the value
-    return __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(v)));
-}
-__device__ __forceinline__ double warp_max(double v) {
+template <int NT> struct BlockComm {
+    static constexpr int W = NT;
+    double* buf;  // [2][NT] exchange slots + [2][NT / 32] reduction slots (8-byte slots for either precision)
+    int flip;
+    __device__ __forceinline__ explicit BlockComm(void* smem) : buf(reinterpret_cast<double*>(smem)), flip(0) {}
+    __host__ __device__ static constexpr int slots() { return 2 * NT + 2 * (NT / 32); }
+    __device__ __forceinline__ int lane() const { return threadIdx.x; }
+    template <typename T> __device__ __forceinline__ T up(T v, int s) {
+        T* b = reinterpret_cast<T*>(buf + flip * NT);
+        b[threadIdx.x] = v;
+        __syncthreads();
+        const T r = (int)threadIdx.x >= s ? b[threadIdx.x - s] : v;
+        flip ^= 1;
+        return r;
+    }
+    template <typename T> __device__ __forceinline__ T dn(T v, int s) {
+        T* b = reinterpret_cast<T*>(buf + flip * NT);
+        b[threadIdx.x] = v;
+        __syncthreads();
+        const T r = (int)threadIdx.x + s < NT ? b[threadIdx.x + s] : v;
+        flip ^= 1;
+        return r;
+    }
+    template <typename T, typename Op> __device__ __forceinline__ T reduce(T v, Op op) {
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, s));
-    return v;
-}
-template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+        for (int s = 16; s > 0; s >>= 1) v = op(v, __shfl_xor_sync(kFull, v, s));
+        T* b = reinterpret_cast<T*>(buf + 2 * NT + flip * (NT / 32));
+        if ((threadIdx.x & 31) == 0) b[threadIdx.x >> 5] = v;
+        __syncthreads();
+        T r = b[0];
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(kFull, v, s);
-    return v;
-}
+        for (int w = 1; w < NT / 32; ++w) r = op(r, b[w]);
+        flip ^= 1;
+        return r;
+    }
+    __device__ __forceinline__ float max(float v) { return reduce(v, [](float a, float b) { return fmaxf(a, b); }); }
+    __device__ __forceinline__ double max(double v) { return reduce(v, [](double a, double b) { return fmax(a, b); }); }
+    template <typename T> __device__ __forceinline__ T sum(T v) { return reduce(v, [](T a, T b) { return a + b; }); }
+    __device__ __forceinline__ bool any(bool p) { return __syncthreads_or(p) != 0; }
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+
 __device__ __forceinline__ float tabs(float v) { return fabsf(v); }   // clears the sign of -0.0 too (redux.max on bits)
 __device__ __forceinline__ double tabs(double v) { return fabs(v); }
-template <typename T> __device__ __forceinline__ T tmax(T a, T b) { return a > b ? a : b; }
-template <typename T> __device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
-__device__ __forceinline__ float trsqrt(float v) { return 1.0f / sqrtf(v); }
+__device__ __forceinline__ float tmax(float a, float b) { return fmaxf(a, b); }   // FMNMX, no compare+select
+__device__ __forceinline__ double tmax(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float tmin(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double tmin(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float trsqrt(float v) { return rsqrtf(v); }  // MUFU.RSQ (2 ulp): scaling factors only
 __device__ __forceinline__ double trsqrt(double v) { return 1.0 / sqrt(v); }
 template <typename T> __device__ __forceinline__ T limit_scaling(T v) {
     v = v < T(kMinScaling) ? T(1) : v;
@@ -110,19 +164,19 @@ template <typename T, int NLEV, int RLEV> struct Factor {
 // per-warp shared constants (read only at termination checks / first iteration): [16][32]
 //   0..2 d | 3..7 D | 8..10 Ed | 11..15 Eb
 constexpr int kConstRows = 16;
-template <int NLEV, int RLEV> __host__ __device__ constexpr int smem_rows_per_warp() { return kConstRows + 18 * (NLEV - RLEV); }
+template <int NLEV, int RLEV> __host__ __device__ constexpr int smem_rows() { return kConstRows + 18 * (NLEV - RLEV); }
 
 template <typename T> __device__ __forceinline__ T tfma(T a, T b, T c);
 template <> __device__ __forceinline__ float tfma<float>(float a, float b, float c) { return fmaf(a, b, c); }
 template <> __device__ __forceinline__ double tfma<double>(double a, double b, double c) { return fma(a, b, c); }
 
 // z = A w for this lane: zd (dynamics block j) and zb (bound rows)
-template <typename T>
-__device__ __forceinline__ void A_apply(const Stage<T>& s, const T w[5], int lane, T zd[3], T zb[5]) {
+template <typename T, typename Comm>
+__device__ __forceinline__ void A_apply(Comm& cm, const Stage<T>& s, const T w[5], int lane, T zd[3], T zb[5]) {
     T o0 = s.a[0] * w[0] + s.a[1] * w[1];
     T o1 = s.a[2] * w[0] + s.a[3] * w[1] + s.a[6] * w[4];
     T o2 = s.a[4] * w[0] + s.a[5] * w[2] + s.a[7] * w[3];
-    o0 = shfl_up(o0, 1); o1 = shfl_up(o1, 1); o2 = shfl_up(o2, 1);
+    o0 = cm.up(o0, 1); o1 = cm.up(o1, 1); o2 = cm.up(o2, 1);
     if (lane == 0) { o0 = T(0); o1 = T(0); o2 = T(0); }
     zd[0] = s.c[0] * w[0] + o0; zd[1] = s.c[1] * w[1] + o1; zd[2] = s.c[2] * w[2] + o2;
 #pragma unroll
@@ -130,9 +184,9 @@ __device__ __forceinline__ void A_apply(const Stage<T>& s, const T w[5], int lan
 }
 
 // r = A' y for this lane's 5 variables
-template <typename T>
-__device__ __forceinline__ void At_apply(const Stage<T>& s, const T yd[3], const T yb[5], T r[5]) {
-    T g0 = shfl_dn(yd[0], 1), g1 = shfl_dn(yd[1], 1), g2 = shfl_dn(yd[2], 1);
+template <typename T, typename Comm>
+__device__ __forceinline__ void At_apply(Comm& cm, const Stage<T>& s, const T yd[3], const T yb[5], T r[5]) {
+    T g0 = cm.dn(yd[0], 1), g1 = cm.dn(yd[1], 1), g2 = cm.dn(yd[2], 1);
     // lanes whose successor is outside the chain have a == 0, so the shuffled value is harmless
     r[0] = s.c[0] * yd[0] + s.a[0] * g0 + s.a[2] * g1 + s.a[4] * g2 + s.e[0] * yb[0];
     r[1] = s.c[1] * yd[1] + s.a[1] * g0 + s.a[3] * g1 + s.e[1] * yb[1];
@@ -142,8 +196,8 @@ __device__ __forceinline__ void At_apply(const Stage<T>& s, const T yd[3], const
 }
 
 // OSQP scale_data (Ruiz equilibration of the KKT matrix + cost scaling), stage layout.
-template <typename T>
-__device__ __forceinline__ void ruiz_scale(Stage<T>& s, int iters, int nvar) {
+template <typename T, typename Comm>
+__device__ __forceinline__ void ruiz_scale(Comm& cm, Stage<T>& s, int iters, int nvar) {
 #pragma unroll
     for (int i = 0; i < 5; ++i) { s.D[i] = T(1); s.Eb[i] = T(1); }
 #pragma unroll
@@ -167,11 +221,11 @@ __device__ __forceinline__ void ruiz_scale(Stage<T>& s, int iters, int nvar) {
         ro[0] = tmax(aa[0], aa[1]);
         ro[1] = tmax(tmax(aa[2], aa[3]), aa[6]);
         ro[2] = tmax(tmax(aa[4], aa[5]), aa[7]);
-        const int lane = threadIdx.x & 31;
+        const int lane = cm.lane();
         T Dt[5], Edt[3], Ebt[5];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            T r = shfl_up(ro[i], 1);
+            T r = cm.up(ro[i], 1);
             if (lane == 0) r = T(0);
             Edt[i] = trsqrt(limit_scaling(tmax(tabs(s.c[i]), r)));
         }
@@ -182,7 +236,7 @@ __device__ __forceinline__ void ruiz_scale(Stage<T>& s, int iters, int nvar) {
         }
         T En[3];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) En[i] = shfl_dn(Edt[i], 1);
+        for (int i = 0; i < 3; ++i) En[i] = cm.dn(Edt[i], 1);
 #pragma unroll
         for (int i = 0; i < 5; ++i) s.P[i] = s.P[i] * Dt[i] * Dt[i];
         s.a[0] = s.a[0] * En[0] * Dt[0]; s.a[1] = s.a[1] * En[0] * Dt[1];
@@ -202,8 +256,8 @@ __device__ __forceinline__ void ruiz_scale(Stage<T>& s, int iters, int nvar) {
         T sp = T(0), mq = T(0);
 #pragma unroll
         for (int i = 0; i < 5; ++i) { sp += tabs(s.P[i]); mq = tmax(mq, tabs(s.q[i])); }
-        sp = warp_sum(sp) / T(nvar);
-        mq = limit_scaling(warp_max(mq));
+        sp = cm.sum(sp) / T(nvar);
+        mq = limit_scaling(cm.max(mq));
         T ct = limit_scaling(tmax(sp, mq));
         ct = T(1) / ct;
 #pragma unroll
@@ -232,16 +286,17 @@ template <typename T> __device__ __forceinline__ void inv3sym(const T* M, T* R) 
 }
 
 // Build S = P + sigma I + A' R A for this lane's stage, eliminate the inputs, PCR-factorise.
-template <typename T, int NLEV, int RLEV>
-__device__ __forceinline__ void factorize(const Stage<T>& s, Factor<T, NLEV, RLEV>& f, T sigma, T rd, const T rb[5],
-                                          int lane, int nstage) {
+template <typename T, int NLEV, int RLEV, typename Comm>
+__device__ __forceinline__ void factorize(Comm& cm, const Stage<T>& s, Factor<T, NLEV, RLEV>& f, T sigma, T rd,
+                                          const T rb[5], int lane, int nstage) {
+    constexpr int W = Comm::W;
     const T* a = s.a;
     T diag[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) diag[i] = s.P[i] + sigma + rb[i] * s.e[i] * s.e[i];
     T cn[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) cn[i] = shfl_dn(s.c[i], 1);
+    for (int i = 0; i < 3; ++i) cn[i] = cm.dn(s.c[i], 1);
     T Dm[9], U[9], Lo[9];
     Dm[0] = diag[0] + rd * (s.c[0] * s.c[0] + a[0] * a[0] + a[2] * a[2] + a[4] * a[4]);
     Dm[4] = diag[1] + rd * (s.c[1] * s.c[1] + a[1] * a[1] + a[3] * a[3]);
@@ -273,7 +328,7 @@ __device__ __forceinline__ void factorize(const Stage<T>& s, Factor<T, NLEV, RLE
             U[3 * i + 2] -= f.iv * f.fv * sxv[i];
             U[3 * i + 1] -= f.ik * f.fk * sxk[i];
         }
-        T add1 = shfl_up(f.ik * f.fk * f.fk, 1), add2 = shfl_up(f.iv * f.fv * f.fv, 1);
+        T add1 = cm.up(f.ik * f.fk * f.fk, 1), add2 = cm.up(f.iv * f.fv * f.fv, 1);
         if (lane > 0) { Dm[4] -= add1; Dm[8] -= add2; }
     }
     // Lo = coupling block (row j, col j-1) = U_{j-1}'
@@ -281,7 +336,7 @@ __device__ __forceinline__ void factorize(const Stage<T>& s, Factor<T, NLEV, RLE
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            T v = shfl_up(U[3 * k + i], 1);
+            T v = cm.up(U[3 * k + i], 1);
             Lo[3 * i + k] = lane > 0 ? v : T(0);
         }
     if (lane >= nstage - 1) {
@@ -300,11 +355,11 @@ __device__ __forceinline__ void factorize(const Stage<T>& s, Factor<T, NLEV, RLE
         T Dup[9], Ddn[9], Uup[9], Ldn[9], Lup[9], Udn[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
-            Dup[i] = shfl_up(Di[i], sft); Ddn[i] = shfl_dn(Di[i], sft);
-            Uup[i] = shfl_up(U[i], sft);  Ldn[i] = shfl_dn(Lo[i], sft);
-            Lup[i] = shfl_up(Lo[i], sft); Udn[i] = shfl_dn(U[i], sft);
+            Dup[i] = cm.up(Di[i], sft); Ddn[i] = cm.dn(Di[i], sft);
+            Uup[i] = cm.up(U[i], sft);  Ldn[i] = cm.dn(Lo[i], sft);
+            Lup[i] = cm.up(Lo[i], sft); Udn[i] = cm.dn(U[i], sft);
         }
-        const bool has_up = lane >= sft, has_dn = lane + sft < 32;
+        const bool has_up = lane >= sft, has_dn = lane + sft < W;
         T al[9], be[9];
         mm3(Lo, Dup, al);
         mm3(U, Ddn, be);
@@ -324,34 +379,35 @@ __device__ __forceinline__ void factorize(const Stage<T>& s, Factor<T, NLEV, RLE
         for (int i = 0; i < 9; ++i) {
             Lo[i] = -t1[i]; U[i] = -t2[i];
             if (lev < RLEV) { f.al[lev < RLEV ? lev : 0][i] = al[i]; f.be[lev < RLEV ? lev : 0][i] = be[i]; }
-            else { f.fs[((lev - RLEV) * 18 + i) * 32 + lane] = al[i]; f.fs[((lev - RLEV) * 18 + 9 + i) * 32 + lane] = be[i]; }
+            else { f.fs[((lev - RLEV) * 18 + i) * W + lane] = al[i]; f.fs[((lev - RLEV) * 18 + 9 + i) * W + lane] = be[i]; }
         }
     }
     T Di[9];
     inv3sym(Dm, Di);
     f.Dinv[0] = Di[0]; f.Dinv[1] = Di[1]; f.Dinv[2] = Di[2]; f.Dinv[3] = Di[4]; f.Dinv[4] = Di[5]; f.Dinv[5] = Di[8];
-    __syncwarp();
+    cm.sync();
 }
 
 // x = S^-1 b
-template <typename T, int NLEV, int RLEV>
-__device__ __forceinline__ void kkt_solve(const Factor<T, NLEV, RLEV>& f, const T b[5], int lane, T x[5]) {
+template <typename T, int NLEV, int RLEV, typename Comm>
+__device__ __forceinline__ void kkt_solve(Comm& cm, const Factor<T, NLEV, RLEV>& f, const T b[5], int lane, T x[5]) {
+    constexpr int W = Comm::W;
     const T bv = f.iv * b[3], bk = f.ik * b[4];
     T bx0 = tfma(-bk, f.sxk0, tfma(-bv, f.sxv0, b[0]));
     T bx1 = tfma(-bk, f.sxk1, b[1]);
     T bx2 = tfma(-bv, f.sxv2, b[2]);
-    T t1 = shfl_up(bk * f.fk, 1), t2 = shfl_up(bv * f.fv, 1);
+    T t1 = cm.up(bk * f.fk, 1), t2 = cm.up(bv * f.fv, 1);
     if (lane > 0) { bx1 -= t1; bx2 -= t2; }
 #pragma unroll
     for (int lev = 0; lev < NLEV; ++lev) {
         const int sft = 1 << lev;
-        const T u0 = shfl_up(bx0, sft), u1 = shfl_up(bx1, sft), u2 = shfl_up(bx2, sft);
-        const T d0 = shfl_dn(bx0, sft), d1 = shfl_dn(bx1, sft), d2 = shfl_dn(bx2, sft);
+        const T u0 = cm.up(bx0, sft), u1 = cm.up(bx1, sft), u2 = cm.up(bx2, sft);
+        const T d0 = cm.dn(bx0, sft), d1 = cm.dn(bx1, sft), d2 = cm.dn(bx2, sft);
         T al[9], be[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
             if (lev < RLEV) { al[i] = f.al[lev < RLEV ? lev : 0][i]; be[i] = f.be[lev < RLEV ? lev : 0][i]; }
-            else { al[i] = f.fs[((lev - RLEV) * 18 + i) * 32 + lane]; be[i] = f.fs[((lev - RLEV) * 18 + 9 + i) * 32 + lane]; }
+            else { al[i] = f.fs[((lev - RLEV) * 18 + i) * W + lane]; be[i] = f.fs[((lev - RLEV) * 18 + 9 + i) * W + lane]; }
         }
         // two independent FMA chains per row (up / down neighbours) keep the dependent depth at 3
         const T p0 = tfma(-al[2], u2, tfma(-al[1], u1, tfma(-al[0], u0, bx0)));
@@ -365,7 +421,7 @@ __device__ __forceinline__ void kkt_solve(const Factor<T, NLEV, RLEV>& f, const 
     x[0] = tfma(f.Dinv[2], bx2, tfma(f.Dinv[1], bx1, f.Dinv[0] * bx0));
     x[1] = tfma(f.Dinv[4], bx2, tfma(f.Dinv[3], bx1, f.Dinv[1] * bx0));
     x[2] = tfma(f.Dinv[5], bx2, tfma(f.Dinv[4], bx1, f.Dinv[2] * bx0));
-    const T xn1 = shfl_dn(x[1], 1), xn2 = shfl_dn(x[2], 1);  // fv, fk are 0 where there is no successor
+    const T xn1 = cm.dn(x[1], 1), xn2 = cm.dn(x[2], 1);  // fv, fk are 0 where there is no successor
     x[3] = f.iv * tfma(-f.fv, xn2, tfma(-f.sxv2, x[2], tfma(-f.sxv0, x[0], b[3])));
     x[4] = f.ik * tfma(-f.fk, xn1, tfma(-f.sxk1, x[1], tfma(-f.sxk0, x[0], b[4])));
 }
@@ -393,10 +449,11 @@ struct SolveResult {
 // is what lets the fp32 path reproduce OSQP's iteration counts and infeasibility certificates.
 // On return w[5] holds the UNSCALED primal stage vector (NaN when OSQP would return no solution).
 // sm: this warp's shared slab, smem_rows_per_warp<NLEV, RLEV>() * 32 elements of T.
-template <typename T, int NLEV, int RLEV>
-__device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSettings& st, int lane, int nstage, int nvar,
-                                                  T* sm, T w[5]) {
-    if (st.scaling > 0) ruiz_scale(s, st.scaling, nvar);
+template <typename T, int NLEV, int RLEV, typename Comm>
+__device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const AdmmSettings& st, int lane, int nstage,
+                                                  int nvar, T* sm, T w[5]) {
+    constexpr int W = Comm::W;
+    if (st.scaling > 0) ruiz_scale(cm, s, st.scaling, nvar);
     else {
 #pragma unroll
         for (int i = 0; i < 5; ++i) { s.D[i] = T(1); s.Eb[i] = T(1); }
@@ -410,20 +467,20 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
         s.ctype[i] = (s.lo[i] < -thr && s.hi[i] > thr) ? -1 : ((s.hi[i] - s.lo[i] < T(kRhoTol)) ? 1 : 0);
     // constants that are only needed at checks go to shared memory
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { sm[i * 32 + lane] = s.d[i]; sm[(8 + i) * 32 + lane] = s.Ed[i]; }
+    for (int i = 0; i < 3; ++i) { sm[i * W + lane] = s.d[i]; sm[(8 + i) * W + lane] = s.Ed[i]; }
 #pragma unroll
-    for (int i = 0; i < 5; ++i) { sm[(3 + i) * 32 + lane] = s.D[i]; sm[(11 + i) * 32 + lane] = s.Eb[i]; }
+    for (int i = 0; i < 5; ++i) { sm[(3 + i) * W + lane] = s.D[i]; sm[(11 + i) * W + lane] = s.Eb[i]; }
     T rho = T(st.rho), rd, rb[5], rbi[5];
     const T sigma = T(st.sigma), alpha = T(st.alpha);
     set_rho(s, rho, rd, rb, rbi);
     Factor<T, NLEV, RLEV> f;
-    f.fs = sm + kConstRows * 32;
-    factorize<T, NLEV, RLEV>(s, f, sigma, rd, rb, lane, nstage);
+    f.fs = sm + kConstRows * W;
+    factorize<T, NLEV, RLEV>(cm, s, f, sigma, rd, rb, lane, nstage);
     // constant norms
     T nq_s = T(0), nq_u = T(0);
 #pragma unroll
     for (int i = 0; i < 5; ++i) { nq_s = tmax(nq_s, tabs(s.q[i])); nq_u = tmax(nq_u, tabs(s.q[i] / s.D[i])); }
-    nq_s = warp_max(nq_s); nq_u = warp_max(nq_u);
+    nq_s = cm.max(nq_s); nq_u = cm.max(nq_u);
     const T cinv = T(1) / s.cs;
     // the loop keeps only a, c, e, P, q, lo, hi of the stage live
     T x[5] = {0, 0, 0, 0, 0}, zb[5] = {0, 0, 0, 0, 0}, yd[3] = {0, 0, 0}, yb[5] = {0, 0, 0, 0, 0};
@@ -437,19 +494,19 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
         for (int i = 0; i < 3; ++i) td[i] = tfma(rd, rdy[i], yd[i]);
 #pragma unroll
         for (int i = 0; i < 5; ++i) tb[i] = tfma(rb[i], rbd[i], yb[i]);
-        At_apply(s, td, tb, g);
+        At_apply(cm, s, td, tb, g);
 #pragma unroll
         for (int i = 0; i < 5; ++i) g[i] = -(tfma(s.P[i], x[i], s.q[i]) + g[i]);
-        kkt_solve<T, NLEV, RLEV>(f, g, lane, dl);
+        kkt_solve<T, NLEV, RLEV>(cm, f, g, lane, dl);
         T add[3], adb[5];
-        A_apply(s, dl, lane, add, adb);
+        A_apply(cm, s, dl, lane, add, adb);
         T dx[5], dyd[3], dyb[5];
 #pragma unroll
         for (int i = 0; i < 5; ++i) { dx[i] = alpha * dl[i]; x[i] += dx[i]; }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const T wv = alpha * (rdy[i] + add[i]);          // v - z_prev
-            const T step = iter == 1 ? sm[i * 32 + lane] : T(0);  // z jumps from the cold start 0 to d once
+            const T step = iter == 1 ? sm[i * W + lane] : T(0);  // z jumps from the cold start 0 to d once
             dyd[i] = rd * (wv - step);
             yd[i] += dyd[i];
             rdy[i] = tfma(alpha, add[i], rdy[i]) - step;
@@ -470,11 +527,11 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
         if (can_check || can_adapt) {
             T axd[3], axb[5], aty[5], zd[3], D[5], Ed[3], Eb[5];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) { zd[i] = sm[i * 32 + lane]; Ed[i] = sm[(8 + i) * 32 + lane]; }
+            for (int i = 0; i < 3; ++i) { zd[i] = sm[i * W + lane]; Ed[i] = sm[(8 + i) * W + lane]; }
 #pragma unroll
-            for (int i = 0; i < 5; ++i) { D[i] = sm[(3 + i) * 32 + lane]; Eb[i] = sm[(11 + i) * 32 + lane]; }
-            A_apply(s, x, lane, axd, axb);
-            At_apply(s, yd, yb, aty);
+            for (int i = 0; i < 5; ++i) { D[i] = sm[(3 + i) * W + lane]; Eb[i] = sm[(11 + i) * W + lane]; }
+            A_apply(cm, s, x, lane, axd, axb);
+            At_apply(cm, s, yd, yb, aty);
             // scaled and unscaled infinity norms
             T pr_s = 0, pr_u = 0, nz_s = 0, nz_u = 0, nax_s = 0, nax_u = 0;
 #pragma unroll
@@ -500,9 +557,9 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
                 npx_s = tmax(npx_s, tabs(px)); npx_u = tmax(npx_u, tabs(px) * di);
                 naty_s = tmax(naty_s, tabs(aty[i])); naty_u = tmax(naty_u, tabs(aty[i]) * di);
             }
-            pr_s = warp_max(pr_s); pr_u = warp_max(pr_u); du_s = warp_max(du_s); du_u = warp_max(du_u) * cinv;
-            nz_s = warp_max(nz_s); nz_u = warp_max(nz_u); nax_s = warp_max(nax_s); nax_u = warp_max(nax_u);
-            npx_s = warp_max(npx_s); npx_u = warp_max(npx_u); naty_s = warp_max(naty_s); naty_u = warp_max(naty_u);
+            pr_s = cm.max(pr_s); pr_u = cm.max(pr_u); du_s = cm.max(du_s); du_u = cm.max(du_u) * cinv;
+            nz_s = cm.max(nz_s); nz_u = cm.max(nz_u); nax_s = cm.max(nax_s); nax_u = cm.max(nax_u);
+            npx_s = cm.max(npx_s); npx_u = cm.max(npx_u); naty_s = cm.max(naty_s); naty_u = cm.max(naty_u);
             if (can_check) {
                 if (pr_u > T(kOsqpInfty) || du_u > T(kOsqpInfty)) { status = -7; break; }
                 const T eps_prim = T(st.eps_abs) + T(st.eps_rel) * tmax(nz_u, nax_u);
@@ -527,14 +584,14 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
                         ndy = tmax(ndy, tabs(Eb[i] * d));
                         lhs += s.hi[i] * tmax(d, T(0)) + s.lo[i] * tmin(d, T(0));
                     }
-                    ndy = warp_max(ndy);
-                    lhs = warp_sum(lhs);
+                    ndy = cm.max(ndy);
+                    lhs = cm.sum(lhs);
                     if (ndy > epi && lhs < -epi * ndy) {
                         T atdy[5], na = 0;
-                        At_apply(s, dyd, pyb, atdy);
+                        At_apply(cm, s, dyd, pyb, atdy);
 #pragma unroll
                         for (int i = 0; i < 5; ++i) na = tmax(na, tabs(atdy[i] / D[i]));
-                        na = warp_max(na);
+                        na = cm.max(na);
                         pinf = na < epi * ndy;
                     }
                 }
@@ -543,16 +600,16 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
                     T ndx = 0, qdx = 0;
 #pragma unroll
                     for (int i = 0; i < 5; ++i) { ndx = tmax(ndx, tabs(D[i] * dx[i])); qdx += s.q[i] * dx[i]; }
-                    ndx = warp_max(ndx);
-                    qdx = warp_sum(qdx);
+                    ndx = cm.max(ndx);
+                    qdx = cm.sum(qdx);
                     if (ndx > edi && qdx < -s.cs * edi * ndx) {
                         T npdx = 0;
 #pragma unroll
                         for (int i = 0; i < 5; ++i) npdx = tmax(npdx, tabs(s.P[i] * dx[i] / D[i]));
-                        npdx = warp_max(npdx);
+                        npdx = cm.max(npdx);
                         if (npdx < s.cs * edi * ndx) {
                             T adxd[3], adxb[5];
-                            A_apply(s, dx, lane, adxd, adxb);
+                            A_apply(cm, s, dx, lane, adxd, adxb);
                             int bad = 0;
 #pragma unroll
                             for (int i = 0; i < 3; ++i) {
@@ -564,7 +621,7 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
                                 T v = adxb[i] / Eb[i];
                                 if ((s.hi[i] < thr && v > edi * ndx) || (s.lo[i] > -thr && v < -edi * ndx)) bad = 1;
                             }
-                            dinf = !__any_sync(kFull, bad);
+                            dinf = !cm.any(bad != 0);
                         }
                     }
                 }
@@ -579,39 +636,39 @@ __device__ __forceinline__ SolveResult admm_solve(Stage<T>& s, const AdmmSetting
                 if (rnew > rho * T(st.adaptive_rho_tolerance) || rnew < rho / T(st.adaptive_rho_tolerance)) {
                     rho = rnew;
                     set_rho(s, rho, rd, rb, rbi);
-                    factorize<T, NLEV, RLEV>(s, f, sigma, rd, rb, lane, nstage);
+                    factorize<T, NLEV, RLEV>(cm, s, f, sigma, rd, rb, lane, nstage);
                 }
             }
         }
     }
     T D[5];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) D[i] = sm[(3 + i) * 32 + lane];
+    for (int i = 0; i < 5; ++i) D[i] = sm[(3 + i) * W + lane];
     if (status == 0) {
         // max_iter reached: OSQP re-checks the residuals with 10x looser tolerances ("approximate"
         // termination) and reports solved-inaccurate (2) or max-iter (-2).  Either way it RETURNS
         // the iterate, which is all the reference looks at (MPC.py:185-206).
         iter = st.max_iter;
         T axd[3], axb[5], aty[5];
-        A_apply(s, x, lane, axd, axb);
-        At_apply(s, yd, yb, aty);
+        A_apply(cm, s, x, lane, axd, axb);
+        At_apply(cm, s, yd, yb, aty);
         T pr_u = 0, nz_u = 0, nax_u = 0, du_u = 0, npx_u = 0, naty_u = 0;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const T ei = T(1) / sm[(8 + i) * 32 + lane], zdi = sm[i * 32 + lane];
+            const T ei = T(1) / sm[(8 + i) * W + lane], zdi = sm[i * W + lane];
             pr_u = tmax(pr_u, tabs(axd[i] - zdi) * ei); nz_u = tmax(nz_u, tabs(zdi) * ei);
             nax_u = tmax(nax_u, tabs(axd[i]) * ei);
         }
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            const T ei = T(1) / sm[(11 + i) * 32 + lane], di = T(1) / D[i], px = s.P[i] * x[i];
+            const T ei = T(1) / sm[(11 + i) * W + lane], di = T(1) / D[i], px = s.P[i] * x[i];
             pr_u = tmax(pr_u, tabs(axb[i] - zb[i]) * ei); nz_u = tmax(nz_u, tabs(zb[i]) * ei);
             nax_u = tmax(nax_u, tabs(axb[i]) * ei);
             du_u = tmax(du_u, tabs(px + s.q[i] + aty[i]) * di); npx_u = tmax(npx_u, tabs(px) * di);
             naty_u = tmax(naty_u, tabs(aty[i]) * di);
         }
-        pr_u = warp_max(pr_u); nz_u = warp_max(nz_u); nax_u = warp_max(nax_u);
-        du_u = warp_max(du_u) * cinv; npx_u = warp_max(npx_u); naty_u = warp_max(naty_u);
+        pr_u = cm.max(pr_u); nz_u = cm.max(nz_u); nax_u = cm.max(nax_u);
+        du_u = cm.max(du_u) * cinv; npx_u = cm.max(npx_u); naty_u = cm.max(naty_u);
         const T eps_prim = T(10) * T(st.eps_abs) + T(10) * T(st.eps_rel) * tmax(nz_u, nax_u);
         const T eps_dual = T(10) * T(st.eps_abs) + T(10) * T(st.eps_rel) * cinv * tmax(tmax(nq_u, naty_u), npx_u);
         status = (pr_u < eps_prim && du_u < eps_dual) ? 2 : -2;

@@ -126,7 +126,7 @@ const char* mpc_last_error(void) { return g_err.c_str(); }
 int mpc_abi_version(void) { return MPC_B200_ABI_VERSION; }
 
 static int validate_cfg(const mpc_config* c) {
-    if (c->N < 3 || c->N > 31) return fail(MPC_E_UNSUPPORTED, "horizon N must be in [3, 31] in this build");
+    if (c->N < 3 || c->N > 127) return fail(MPC_E_UNSUPPORTED, "horizon N must be in [3, 127]");
     if (!(c->car_length > 0) || !(c->Ts > 0)) return fail(MPC_E_INVALID, "car_length and Ts must be positive");
     if (c->precision != 0 && c->precision != 1) return fail(MPC_E_INVALID, "precision must be 0 (fp32) or 1 (fp64)");
     if (c->max_iter < 1 || c->check_termination < 0 || c->adaptive_rho_interval < 0 || c->scaling < 0)

@@ -311,5 +311,38 @@ def test_errors_are_reported_not_swallowed(track):
     with pytest.raises(mpc_b200.MpcError, match="mpc_set_path"):
         eng.raycast(_t([0], torch.int32), _t(np.zeros((1, 30))), _t(np.zeros((1, 30))))
     with pytest.raises(mpc_b200.MpcError):
-        mpc_b200.Engine(N=64)   # horizons above 31 stages are not built yet: loud, not silent
+        mpc_b200.Engine(N=200)  # horizons above 127 stages are not supported: loud, not silent
     eng.close()
+
+
+@pytest.mark.parametrize("N,precision", [(10, 1), (50, 1), (100, 1), (10, 0), (50, 0)])
+def test_other_horizons_full_step(engine_factory, track, orc, orc_path, N, precision):
+    """BASELINE configs 4/5 horizons.  N + 1 <= 32 runs warp-per-scenario, longer horizons block-per-scenario
+    (shared-memory exchange); both must reproduce the oracle's step: widths bit-exact, same solver trace."""
+    TF = load_golden("teacher_forced.npz")
+    B = 12
+    rng = np.random.default_rng(N)
+    ctrl = np.zeros((B, 2 * N))
+    ctrl[::2, 0::2] = rng.uniform(0.3, 1.0, (B // 2, N))
+    ctrl[::2, 1::2] = rng.uniform(-0.4, 0.4, (B // 2, N))
+    st0 = np.ascontiguousarray(TF["state"][:B].T)
+    eng = engine_factory(N=N, precision=precision)
+    eng.scenarios_init(st0)
+    eng.scenarios_set_state(st0, ctrl, None)
+    eng.step()
+    o = eng.scenarios_read()
+    kmax = np.tan(0.66) / 0.12
+    cfg = orc.mpc_cfg(N, [1.0, 0.0, 0.0], [0.5, 0.0], [1.0, 0.0, 0.0], [-np.inf] * 3, [np.inf] * 3, [0.0, -kmax],
+                      [1.0, kmax], 4.0, 0.12, 0.06 / np.sqrt(2))
+    world = orc.World(orc_path, cfg, track.grid.shape, track.origin, track.res, 0.05)
+    orc.set_pow_mode(False)
+    for b in range(B):
+        r = world.step(track.grid_obs, TF["state"][b], ctrl[b], 0)
+        assert r["wp_id"] == o["wp_id"][b]
+        assert np.array_equal(r["ub"], o["ub"][b]) and np.array_equal(r["lb"], o["lb"][b])
+        assert r["qp_status"] == o["qp_status"][b], (b, r["qp_status"], o["qp_status"][b])
+        if precision == 1 or N <= 31:
+            assert r["iters"] == o["iters"][b], (b, r["iters"], o["iters"][b])
+        tol = 1e-7 if precision == 1 else QP_TOL
+        assert np.abs(r["u"] - o["u"][b]).max() <= tol
+        assert np.abs(r["state"] - o["state"][:, b]).max() <= tol
