@@ -40,12 +40,16 @@ def load_track():
     return T, grid
 
 
-def scenario_states(T, B, lo, hi, seed=2):
-    """C2 of SURVEY.md section 8d: all B scenarios are generated identically on every rank, then sliced."""
+def scenario_states(T, B, lo, hi, seed=2, kind="tracking", return_obstacles=False):
+    """C2 / C3 of SURVEY.md section 8d: all B scenarios are generated identically on every rank, then sliced."""
     from mpc_b200 import distributed as D
     # start waypoints U{0..119}: 80 waypoints (3.5 m = 70+ steps at 1 m/s) of headroom before s >= length would
     # end a car's lap (simulation.py:134), so every car is live in every timed step
-    sc = D.make_scenarios(len(T["wp_x"]), B, seed=seed, max_start_wp=len(T["wp_x"]) - 80)
+    sc = D.make_scenarios(len(T["wp_x"]), B, seed=seed, max_start_wp=len(T["wp_x"]) - 80, kind=kind,
+                          wp_xy_psi=(T["wp_x"], T["wp_y"], T["wp_psi"]))
+    if return_obstacles:
+        off = sc["obs_off"]
+        return sc["obs"][off[lo]:off[hi]], (off[lo:hi + 1] - off[lo]).astype(np.int32)
     w = sc["start_wp"][lo:hi]
     e_y, e_psi = sc["e_y"][lo:hi], sc["e_psi"][lo:hi]
     lc = np.cumsum(T["segment_lengths"])
@@ -162,6 +166,9 @@ def main():
     ap.add_argument("--precision", type=int, default=0, help="0 = fp32 ADMM (production), 1 = fp64")
     ap.add_argument("--cpu-sample", type=int, default=768, help="cars in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="tracking", choices=["tracking", "obstacles"],
+                    help="tracking = BASELINE configs[1] (headline); obstacles = configs[2] style: per-scenario random "
+                         "obstacle sets, per-step raycast on per-scenario grids (use --batch 8192, seed 3)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -187,7 +194,9 @@ def main():
     Bg = args.batch * world                      # weak scaling: fixed work per GPU
     lo, hi = D.shard_range(Bg, rank, world)
     B = hi - lo
-    states = scenario_states(T, Bg, lo, hi)
+    kind, seed = ("obstacles", 3) if args.workload == "obstacles" else ("tracking", 2)
+    states = scenario_states(T, Bg, lo, hi, seed=seed, kind=kind)
+    obstacles = scenario_states(T, Bg, lo, hi, seed=seed, kind=kind, return_obstacles=True) if kind == "obstacles" else None
     tab = _lib.path_table(T["wp_x"], T["wp_y"], T["wp_psi"], T["wp_kappa"], T["wp_vref"])
     lc = np.cumsum(T["segment_lengths"])
 
@@ -195,6 +204,8 @@ def main():
         e = mpc_b200.Engine(precision=args.precision)
         e.set_path(tab, lc, T["border"], True)
         e.set_base_grid(grid, T["origin"], float(T["resolution"]))
+        if obstacles is not None:
+            e.set_obstacles(obstacles[0], obstacles[1])
         e.scenarios_init(states)
         return e
 
@@ -278,7 +289,7 @@ def main():
 
     # ---------------- CPU baseline: the oracle port on a bounded sample, rank 0, N = 1 only --------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and obstacles is None:
         sample = min(args.cpu_sample, B)
         v, dt, nthr, _ = time_cpu_port(T, grid, states[:, :sample], 2)
         cpu = {"value": v, "unit": UNIT, "cores": nthr, "kind": "port",
@@ -290,8 +301,11 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == 0 else "f64", "data": "synthetic",
-            "config": {"workload": "path tracking, %d cars/GPU on sim_map, randomised start offsets (seed 2), N=30 "
-                                   "(BASELINE configs[1]); one step = localise+raycast+QP solve+rollout for every car" % args.batch,
+            "config": {"workload": ("path tracking, %d cars/GPU on sim_map, randomised start offsets (seed 2), N=30 "
+                                    "(BASELINE configs[1]); one step = localise+raycast+QP solve+rollout for every car" % args.batch)
+                       if obstacles is None else
+                       ("obstacle avoidance, %d scenarios/GPU with randomised obstacle sets (seed 3), per-step raycast on "
+                        "per-scenario grids, N=30 (BASELINE configs[2] style)" % args.batch),
                        "horizon": N_HORIZON, "batch_per_gpu": args.batch, "global_batch": Bg, "eps_abs": 1e-3,
                        "eps_rel": 1e-3, "cold_start": True, "l2": "flushed between timed steps (256 MB fill)",
                        "parallelism": "scenario shards, no data-path collective"},

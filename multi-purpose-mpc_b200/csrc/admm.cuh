@@ -161,9 +161,9 @@ template <typename T, int NLEV, int RLEV> struct Factor {
     T fv, fk;              // coupling of (v, kappa)_j to (t, e_psi)_{j+1}
 };
 
-// per-warp shared constants (read only at termination checks / first iteration): [16][32]
-//   0..2 d | 3..7 D | 8..10 Ed | 11..15 Eb
-constexpr int kConstRows = 16;
+// per-scenario shared constants (read only at termination checks): [29][W]
+//   0..2 d | 3..7 D | 8..10 Ed | 11..15 Eb | 16..20 1/D | 21..23 1/Ed | 24..28 1/Eb
+constexpr int kConstRows = 29;
 template <int NLEV, int RLEV> __host__ __device__ constexpr int smem_rows() { return kConstRows + 18 * (NLEV - RLEV); }
 
 template <typename T> __device__ __forceinline__ T tfma(T a, T b, T c);
@@ -467,9 +467,12 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
         s.ctype[i] = (s.lo[i] < -thr && s.hi[i] > thr) ? -1 : ((s.hi[i] - s.lo[i] < T(kRhoTol)) ? 1 : 0);
     // constants that are only needed at checks go to shared memory
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { sm[i * W + lane] = s.d[i]; sm[(8 + i) * W + lane] = s.Ed[i]; }
+    for (int i = 0; i < 3; ++i) { sm[i * W + lane] = s.d[i]; sm[(8 + i) * W + lane] = s.Ed[i]; sm[(21 + i) * W + lane] = T(1) / s.Ed[i]; }
 #pragma unroll
-    for (int i = 0; i < 5; ++i) { sm[(3 + i) * W + lane] = s.D[i]; sm[(11 + i) * W + lane] = s.Eb[i]; }
+    for (int i = 0; i < 5; ++i) {
+        sm[(3 + i) * W + lane] = s.D[i]; sm[(11 + i) * W + lane] = s.Eb[i];
+        sm[(16 + i) * W + lane] = T(1) / s.D[i]; sm[(24 + i) * W + lane] = T(1) / s.Eb[i];
+    }
     T rho = T(st.rho), rd, rb[5], rbi[5];
     const T sigma = T(st.sigma), alpha = T(st.alpha);
     set_rho(s, rho, rd, rb, rbi);
@@ -479,12 +482,13 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
     // constant norms
     T nq_s = T(0), nq_u = T(0);
 #pragma unroll
-    for (int i = 0; i < 5; ++i) { nq_s = tmax(nq_s, tabs(s.q[i])); nq_u = tmax(nq_u, tabs(s.q[i] / s.D[i])); }
+    for (int i = 0; i < 5; ++i) { nq_s = tmax(nq_s, tabs(s.q[i])); nq_u = tmax(nq_u, tabs(s.q[i]) * sm[(16 + i) * W + lane]); }
     nq_s = cm.max(nq_s); nq_u = cm.max(nq_u);
     const T cinv = T(1) / s.cs;
     // the loop keeps only a, c, e, P, q, lo, hi of the stage live
     T x[5] = {0, 0, 0, 0, 0}, zb[5] = {0, 0, 0, 0, 0}, yd[3] = {0, 0, 0}, yb[5] = {0, 0, 0, 0, 0};
     T rdy[3] = {0, 0, 0}, rbd[5] = {0, 0, 0, 0, 0};  // tracked residuals A x - z
+    T stepd[3] = {s.d[0], s.d[1], s.d[2]};            // z jumps from the cold start 0 to d in iteration 1, then stays
     int status = 0, iter = 0;
     int chk = st.check_termination > 0 ? st.check_termination : -1;
     int adp = st.adaptive_rho_interval > 0 ? st.adaptive_rho_interval : -1;
@@ -500,24 +504,24 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
         kkt_solve<T, NLEV, RLEV>(cm, f, g, lane, dl);
         T add[3], adb[5];
         A_apply(cm, s, dl, lane, add, adb);
-        T dx[5], dyd[3], dyb[5];
+        T ed[3], eb[5];  // (v - z_prev) - (z_new - z_prev): dy = rho * e
 #pragma unroll
-        for (int i = 0; i < 5; ++i) { dx[i] = alpha * dl[i]; x[i] += dx[i]; }
+        for (int i = 0; i < 5; ++i) x[i] = tfma(alpha, dl[i], x[i]);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const T wv = alpha * (rdy[i] + add[i]);          // v - z_prev
-            const T step = iter == 1 ? sm[i * W + lane] : T(0);  // z jumps from the cold start 0 to d once
-            dyd[i] = rd * (wv - step);
-            yd[i] += dyd[i];
-            rdy[i] = tfma(alpha, add[i], rdy[i]) - step;
+            const T wv = alpha * (rdy[i] + add[i]);  // v - z_prev
+            ed[i] = wv - stepd[i];
+            yd[i] = tfma(rd, ed[i], yd[i]);
+            rdy[i] = tfma(alpha, add[i], rdy[i]) - stepd[i];
+            stepd[i] = T(0);
         }
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
             const T wv = alpha * (rbd[i] + adb[i]);
             const T zn = tmin(tmax(tfma(rbi[i], yb[i], zb[i] + wv), s.lo[i]), s.hi[i]);
             const T step = zn - zb[i];
-            dyb[i] = rb[i] * (wv - step);
-            yb[i] += dyb[i];
+            eb[i] = wv - step;
+            yb[i] = tfma(rb[i], eb[i], yb[i]);
             rbd[i] = tfma(alpha, adb[i], rbd[i]) - step;
             zb[i] = zn;
         }
@@ -525,25 +529,32 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
         if (can_check) chk = st.check_termination;
         if (can_adapt) adp = st.adaptive_rho_interval;
         if (can_check || can_adapt) {
-            T axd[3], axb[5], aty[5], zd[3], D[5], Ed[3], Eb[5];
+            T axd[3], axb[5], aty[5], zd[3], D[5], Ed[3], Eb[5], Di[5], Edi[3], Ebi[5], dx[5], dyd[3], dyb[5];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) { zd[i] = sm[i * W + lane]; Ed[i] = sm[(8 + i) * W + lane]; }
+            for (int i = 0; i < 3; ++i) {
+                zd[i] = sm[i * W + lane]; Ed[i] = sm[(8 + i) * W + lane]; Edi[i] = sm[(21 + i) * W + lane];
+                dyd[i] = rd * ed[i];
+            }
 #pragma unroll
-            for (int i = 0; i < 5; ++i) { D[i] = sm[(3 + i) * W + lane]; Eb[i] = sm[(11 + i) * W + lane]; }
+            for (int i = 0; i < 5; ++i) {
+                D[i] = sm[(3 + i) * W + lane]; Eb[i] = sm[(11 + i) * W + lane];
+                Di[i] = sm[(16 + i) * W + lane]; Ebi[i] = sm[(24 + i) * W + lane];
+                dx[i] = alpha * dl[i]; dyb[i] = rb[i] * eb[i];
+            }
             A_apply(cm, s, x, lane, axd, axb);
             At_apply(cm, s, yd, yb, aty);
             // scaled and unscaled infinity norms
             T pr_s = 0, pr_u = 0, nz_s = 0, nz_u = 0, nax_s = 0, nax_u = 0;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                T r = tabs(axd[i] - zd[i]), ei = T(1) / Ed[i];
+                T r = tabs(axd[i] - zd[i]), ei = Edi[i];
                 pr_s = tmax(pr_s, r); pr_u = tmax(pr_u, r * ei);
                 nz_s = tmax(nz_s, tabs(zd[i])); nz_u = tmax(nz_u, tabs(zd[i]) * ei);
                 nax_s = tmax(nax_s, tabs(axd[i])); nax_u = tmax(nax_u, tabs(axd[i]) * ei);
             }
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
-                T r = tabs(axb[i] - zb[i]), ei = T(1) / Eb[i];
+                T r = tabs(axb[i] - zb[i]), ei = Ebi[i];
                 pr_s = tmax(pr_s, r); pr_u = tmax(pr_u, r * ei);
                 nz_s = tmax(nz_s, tabs(zb[i])); nz_u = tmax(nz_u, tabs(zb[i]) * ei);
                 nax_s = tmax(nax_s, tabs(axb[i])); nax_u = tmax(nax_u, tabs(axb[i]) * ei);
@@ -551,7 +562,7 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
             T du_s = 0, du_u = 0, npx_s = 0, npx_u = 0, naty_s = 0, naty_u = 0;
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
-                T px = s.P[i] * x[i], di = T(1) / D[i];
+                T px = s.P[i] * x[i], di = Di[i];
                 T r = tabs(px + s.q[i] + aty[i]);
                 du_s = tmax(du_s, r); du_u = tmax(du_u, r * di);
                 npx_s = tmax(npx_s, tabs(px)); npx_u = tmax(npx_u, tabs(px) * di);
@@ -590,7 +601,7 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
                         T atdy[5], na = 0;
                         At_apply(cm, s, dyd, pyb, atdy);
 #pragma unroll
-                        for (int i = 0; i < 5; ++i) na = tmax(na, tabs(atdy[i] / D[i]));
+                        for (int i = 0; i < 5; ++i) na = tmax(na, tabs(atdy[i] * Di[i]));
                         na = cm.max(na);
                         pinf = na < epi * ndy;
                     }
@@ -605,7 +616,7 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
                     if (ndx > edi && qdx < -s.cs * edi * ndx) {
                         T npdx = 0;
 #pragma unroll
-                        for (int i = 0; i < 5; ++i) npdx = tmax(npdx, tabs(s.P[i] * dx[i] / D[i]));
+                        for (int i = 0; i < 5; ++i) npdx = tmax(npdx, tabs(s.P[i] * dx[i] * Di[i]));
                         npdx = cm.max(npdx);
                         if (npdx < s.cs * edi * ndx) {
                             T adxd[3], adxb[5];
@@ -613,12 +624,12 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
                             int bad = 0;
 #pragma unroll
                             for (int i = 0; i < 3; ++i) {
-                                T v = adxd[i] / Ed[i];
+                                T v = adxd[i] * Edi[i];
                                 if (v > edi * ndx || v < -edi * ndx) bad = 1;  // equality rows have finite bounds
                             }
 #pragma unroll
                             for (int i = 0; i < 5; ++i) {
-                                T v = adxb[i] / Eb[i];
+                                T v = adxb[i] * Ebi[i];
                                 if ((s.hi[i] < thr && v > edi * ndx) || (s.lo[i] > -thr && v < -edi * ndx)) bad = 1;
                             }
                             dinf = !cm.any(bad != 0);
@@ -655,13 +666,13 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
         T pr_u = 0, nz_u = 0, nax_u = 0, du_u = 0, npx_u = 0, naty_u = 0;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const T ei = T(1) / sm[(8 + i) * W + lane], zdi = sm[i * W + lane];
+            const T ei = sm[(21 + i) * W + lane], zdi = sm[i * W + lane];
             pr_u = tmax(pr_u, tabs(axd[i] - zdi) * ei); nz_u = tmax(nz_u, tabs(zdi) * ei);
             nax_u = tmax(nax_u, tabs(axd[i]) * ei);
         }
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            const T ei = T(1) / sm[(11 + i) * W + lane], di = T(1) / D[i], px = s.P[i] * x[i];
+            const T ei = sm[(24 + i) * W + lane], di = sm[(16 + i) * W + lane], px = s.P[i] * x[i];
             pr_u = tmax(pr_u, tabs(axb[i] - zb[i]) * ei); nz_u = tmax(nz_u, tabs(zb[i]) * ei);
             nax_u = tmax(nax_u, tabs(axb[i]) * ei);
             du_u = tmax(du_u, tabs(px + s.q[i] + aty[i]) * di); npx_u = tmax(npx_u, tabs(px) * di);
