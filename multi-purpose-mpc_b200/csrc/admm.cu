@@ -6,13 +6,13 @@
 
 namespace mpcb {
 
-constexpr int kWarpsPerBlock = 2;
+constexpr int kWarpsPerBlock = 1;
 
 // Tuning point per precision: RLEV = PCR levels kept in registers (the rest in shared memory),
 // MINB = minimum resident blocks per SM handed to __launch_bounds__ (caps registers per thread).
 template <typename T> struct Tune;
-template <> struct Tune<float> { static constexpr int rlev = 5, minb = 4; };
-template <> struct Tune<double> { static constexpr int rlev = 0, minb = 4; };
+template <> struct Tune<float> { static constexpr int rlev = 5, minb = 8; };
+template <> struct Tune<double> { static constexpr int rlev = 0, minb = 8; };
 template <int NLEV, int RLEV> constexpr int clamp_rlev() { return RLEV < NLEV ? RLEV : NLEV; }
 template <typename T, int NLEV, int RLEV> constexpr size_t warp_smem_bytes() {
     return (size_t)kWarpsPerBlock * smem_rows<NLEV, RLEV>() * 32 * sizeof(T);
