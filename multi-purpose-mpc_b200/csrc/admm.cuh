@@ -441,7 +441,7 @@ struct SolveResult {
 
 // The OSQP loop for one scenario (all 32 lanes of the warp call this together), in "increment form":
 // instead of x~ the linear solve returns D = x~ - x,
-//     S D = -(q + P x + A'(y + R r)),      r = A x - z  (tracked, never recomputed from x),
+//     S D = -(q + P x + t + A'(R r)),   r = A x - z and t = A'y both TRACKED (r += ..., t += A'dy), never recomputed,
 // and the row updates use  v - z = alpha (r + A D),  z+ = clip(z + (v - z) + y / rho),
 // dy = rho ((v - z) - (z+ - z)),  r+ = r + alpha A D - (z+ - z).  This is the same iteration as
 // oracle/osqp_oracle.c in exact arithmetic (tools/admm_pcr_model.py checks it), but every quantity
@@ -486,7 +486,8 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
     nq_s = cm.max(nq_s); nq_u = cm.max(nq_u);
     const T cinv = T(1) / s.cs;
     // the loop keeps only a, c, e, P, q, lo, hi of the stage live
-    T x[5] = {0, 0, 0, 0, 0}, zb[5] = {0, 0, 0, 0, 0}, yd[3] = {0, 0, 0}, yb[5] = {0, 0, 0, 0, 0};
+    T x[5] = {0, 0, 0, 0, 0}, zb[5] = {0, 0, 0, 0, 0}, yb[5] = {0, 0, 0, 0, 0};
+    T ty[5] = {0, 0, 0, 0, 0};  // tracked A'y: accumulated from the small dual steps, never recomputed from a large y
     T rdy[3] = {0, 0, 0}, rbd[5] = {0, 0, 0, 0, 0};  // tracked residuals A x - z
     T stepd[3] = {s.d[0], s.d[1], s.d[2]};            // z jumps from the cold start 0 to d in iteration 1, then stays
     int status = 0, iter = 0;
@@ -495,23 +496,22 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
     for (iter = 1; iter <= st.max_iter; ++iter) {
         T g[5], td[3], tb[5], dl[5];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) td[i] = tfma(rd, rdy[i], yd[i]);
+        for (int i = 0; i < 3; ++i) td[i] = rd * rdy[i];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) tb[i] = tfma(rb[i], rbd[i], yb[i]);
+        for (int i = 0; i < 5; ++i) tb[i] = rb[i] * rbd[i];
         At_apply(cm, s, td, tb, g);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) g[i] = -(tfma(s.P[i], x[i], s.q[i]) + g[i]);
+        for (int i = 0; i < 5; ++i) g[i] = -((tfma(s.P[i], x[i], s.q[i]) + ty[i]) + g[i]);
         kkt_solve<T, NLEV, RLEV>(cm, f, g, lane, dl);
         T add[3], adb[5];
         A_apply(cm, s, dl, lane, add, adb);
-        T ed[3], eb[5];  // (v - z_prev) - (z_new - z_prev): dy = rho * e
+        T ed[3], eb[5];  // dual steps dy = rho ((v - z_prev) - (z_new - z_prev))
 #pragma unroll
         for (int i = 0; i < 5; ++i) x[i] = tfma(alpha, dl[i], x[i]);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const T wv = alpha * (rdy[i] + add[i]);  // v - z_prev
-            ed[i] = wv - stepd[i];
-            yd[i] = tfma(rd, ed[i], yd[i]);
+            ed[i] = rd * (wv - stepd[i]);  // dy of the dynamics rows (their y itself is never needed)
             rdy[i] = tfma(alpha, add[i], rdy[i]) - stepd[i];
             stepd[i] = T(0);
         }
@@ -520,10 +520,16 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
             const T wv = alpha * (rbd[i] + adb[i]);
             const T zn = tmin(tmax(tfma(rbi[i], yb[i], zb[i] + wv), s.lo[i]), s.hi[i]);
             const T step = zn - zb[i];
-            eb[i] = wv - step;
-            yb[i] = tfma(rb[i], eb[i], yb[i]);
+            eb[i] = rb[i] * (wv - step);  // dy of the bound rows
+            yb[i] += eb[i];
             rbd[i] = tfma(alpha, adb[i], rbd[i]) - step;
             zb[i] = zn;
+        }
+        {
+            T dty[5];
+            At_apply(cm, s, ed, eb, dty);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) ty[i] += dty[i];
         }
         const bool can_check = (--chk == 0), can_adapt = (--adp == 0);
         if (can_check) chk = st.check_termination;
@@ -533,16 +539,15 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 zd[i] = sm[i * W + lane]; Ed[i] = sm[(8 + i) * W + lane]; Edi[i] = sm[(21 + i) * W + lane];
-                dyd[i] = rd * ed[i];
+                dyd[i] = ed[i];
             }
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
                 D[i] = sm[(3 + i) * W + lane]; Eb[i] = sm[(11 + i) * W + lane];
                 Di[i] = sm[(16 + i) * W + lane]; Ebi[i] = sm[(24 + i) * W + lane];
-                dx[i] = alpha * dl[i]; dyb[i] = rb[i] * eb[i];
+                dx[i] = alpha * dl[i]; dyb[i] = eb[i]; aty[i] = ty[i];
             }
             A_apply(cm, s, x, lane, axd, axb);
-            At_apply(cm, s, yd, yb, aty);
             // scaled and unscaled infinity norms
             T pr_s = 0, pr_u = 0, nz_s = 0, nz_u = 0, nax_s = 0, nax_u = 0;
 #pragma unroll
@@ -662,7 +667,8 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
         iter = st.max_iter;
         T axd[3], axb[5], aty[5];
         A_apply(cm, s, x, lane, axd, axb);
-        At_apply(cm, s, yd, yb, aty);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) aty[i] = ty[i];
         T pr_u = 0, nz_u = 0, nax_u = 0, du_u = 0, npx_u = 0, naty_u = 0;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {

@@ -356,3 +356,93 @@ def admm(N, Pd, q, Ax, l, u, dtype=np.float64, rho=0.1, sigma=1e-6, alpha=1.6, e
     xs = (D * x).astype(np.float64)
     xout = np.concatenate([xs[:, :3].ravel(), xs[:N, 3:].ravel()])
     return dict(x=xout, iter=it, status=status, rho=float(rho), rho_updates=rho_updates, n_factor=n_fac)
+
+
+# ------------------------------------------------------------------------------------------------------
+# increment ("delta") form -- what csrc/admm.cuh::admm_solve implements
+# ------------------------------------------------------------------------------------------------------
+# The linear solve returns D = x~ - x from  S D = -(q + P x + A'y + A'(R r))  with tracked residuals r = A x - z and
+# a tracked t = A'y (t += A'dy); rows update through  v - z = alpha (r + A D).  Same iterates as admm() in exact arithmetic; in fp32 every
+# quantity multiplied by rho_eq = 1e3 rho is a small residual instead of a difference of O(1) numbers, which is
+# what lets single precision reproduce OSQP's iteration counts and infeasibility certificates at eps = 1e-3.
+def admm_delta(N, Pd, q, Ax, l, u, dtype=np.float32, rho=0.1, sigma=1e-6, alpha=1.6, eps_abs=1e-3, eps_rel=1e-3,
+         eps_prim_inf=1e-4, eps_dual_inf=1e-4, max_iter=4000, scaling=10, check_termination=25,
+         adaptive_rho_interval=25, adaptive_rho_tolerance=5.0, resync=False):
+    dt = np.dtype(dtype); T = dt.type
+    s = from_reference_layout(N, Pd, q, Ax, l, u, dt)
+    L = N + 1
+    mask = np.ones((L, 5), bool); mask[N, 3:] = False
+    s["mask"] = mask
+    s["e"][N, 3:] = 0; s["lo"][N, 3:] = 0; s["hi"][N, 3:] = 0
+    ruiz(s, scaling, 5*N+3)
+    D, Ed, Eb, cs = s["D"], s["Ed"], s["Eb"], s["cs"]
+    lo, hi, dd, qq, P = s["lo"], s["hi"], s["d"], s["q"], s["P"]
+    thr = T(OSQP_INFTY * MIN_SCALING)
+    ctype = np.where((lo < -thr) & (hi > thr), -1, np.where(hi - lo < T(RHO_TOL), 1, 0))
+    def rho_vec(r):
+        return np.where(ctype == -1, T(RHO_MIN), np.where(ctype == 1, T(RHO_EQ_OVER_RHO_INEQ * r), T(r))).astype(dt)
+    rho = T(rho); rb = rho_vec(rho)
+    s["P"][N, 3:] = 1.0; factorize(s, sigma, rho, rb); s["P"][N, 3:] = 0.0
+    rd = T(RHO_EQ_OVER_RHO_INEQ * rho)
+    x = np.zeros((L, 5), dt); zb = np.zeros((L, 5), dt); yd = np.zeros((L, 3), dt); yb = np.zeros((L, 5), dt)
+    # tracked residuals r = A x - z ; cold start x = z = 0 -> r = 0 ; the dynamics z jumps 0 -> d in iteration 1
+    rdy = np.zeros((L, 3), dt); rbd = np.zeros((L, 5), dt)
+    ty = np.zeros((L, 5), dt)  # tracked A'y: accumulated from the small dual steps, never recomputed from y
+    zd = np.zeros((L, 3), dt)
+    al = T(alpha); status = 0
+    for it in range(1, max_iter + 1):
+        g = -(qq + P * x + ty + At_apply(s, rd * rdy, rb * rbd))
+        g = np.where(mask, g, 0).astype(dt)
+        dl = solve(s, g)
+        Add, Adb = A_apply(s, dl)
+        x = (x + al * dl).astype(dt); dx = al*dl
+        # dynamics rows: z_new = d
+        wd = al * (rdy + Add)                 # v - z_prev
+        zdn = dd
+        stepd = zdn - zd                      # exactly 0 after the first iteration
+        dyd = rd * (wd - stepd); yd = (yd + dyd).astype(dt)
+        rdy = (rdy + al * Add - stepd).astype(dt); zd = zdn.copy()
+        # bound rows
+        wb = al * (rbd + Adb)
+        zbn = np.minimum(np.maximum(zb + wb + yb / rb, lo), hi).astype(dt)
+        stepb = (zbn - zb).astype(dt)
+        dyb = rb * (wb - stepb); yb = (yb + dyb).astype(dt)
+        rbd = (rbd + al * Adb - stepb).astype(dt); zb = zbn
+        ty = (ty + At_apply(s, dyd, dyb)).astype(dt)
+        if it % check_termination == 0 or it % adaptive_rho_interval == 0:
+            Axd, Axb = A_apply(s, x)
+            rpd, rpb = Axd - zd, Axb - zb
+            drift = max(np.abs(rpd - rdy).max(), np.abs(rpb - rbd).max())
+            if resync: rdy, rbd = rpd.astype(dt), rpb.astype(dt)
+            Px = P * x; Aty = ty
+            rdual = np.where(mask, Px + qq + Aty, 0)
+            pri_res = max(np.max(np.abs(rpd / Ed)), np.max(np.abs(rpb / Eb)))
+            dua_res = np.max(np.abs(rdual / D)) / cs
+            if it % check_termination == 0:
+                nz_ = max(np.max(np.abs(zd / Ed)), np.max(np.abs(zb / Eb)))
+                nax = max(np.max(np.abs(Axd / Ed)), np.max(np.abs(Axb / Eb)))
+                eps_prim = eps_abs + eps_rel * max(nz_, nax)
+                nd = max(np.max(np.abs(qq / D)), np.max(np.abs(Aty / D)), np.max(np.abs(Px / D))) / cs
+                eps_dual = eps_abs + eps_rel * nd
+                if pri_res < eps_prim and dua_res < eps_dual: status = 1; break
+                if not (pri_res < eps_prim):
+                    pyd = dyd
+                    pyb = np.where(hi > thr, np.where(lo < -thr, 0, np.minimum(dyb, 0)), np.where(lo < -thr, np.maximum(dyb, 0), dyb))
+                    ndy = max(np.max(np.abs(Ed * pyd)), np.max(np.abs(Eb * pyb)))
+                    if ndy > eps_prim_inf:
+                        lhs = np.sum(dd * pyd) + np.sum(hi * np.maximum(pyb, 0) + lo * np.minimum(pyb, 0))
+                        if lhs < -eps_prim_inf * ndy:
+                            Atdy = np.where(mask, At_apply(s, pyd, pyb), 0)
+                            if np.max(np.abs(Atdy / D)) < eps_prim_inf * ndy: status = -3; break
+            if it % adaptive_rho_interval == 0:
+                pn = max(np.abs(rpd).max(), np.abs(rpb).max())
+                pn /= max(np.max(np.abs(zd)), np.max(np.abs(zb)), np.max(np.abs(Axd)), np.max(np.abs(Axb))) + 1e-10
+                dn = np.max(np.abs(rdual)); dn /= max(np.max(np.abs(qq)), np.max(np.abs(Aty)), np.max(np.abs(Px))) + 1e-10
+                rnew = float(rho) * np.sqrt(pn / (dn + 1e-10)); rnew = min(max(rnew, RHO_MIN), RHO_MAX)
+                if rnew > float(rho) * adaptive_rho_tolerance or rnew < float(rho) / adaptive_rho_tolerance:
+                    rho = T(rnew); rb = rho_vec(rho); rd = T(RHO_EQ_OVER_RHO_INEQ * rho)
+                    s["P"][N, 3:] = 1.0; factorize(s, sigma, rho, rb); s["P"][N, 3:] = 0.0
+    if status == 0: status = -2
+    xs = (D * x).astype(np.float64)
+    return dict(x=np.concatenate([xs[:, :3].ravel(), xs[:N, 3:].ravel()]), iter=it, status=status, drift=float(drift))
+
