@@ -199,8 +199,8 @@ def test_teacher_forced_step(engine_factory, precision):
     tol = QP_TOL if precision == 0 else 1e-8
     assert np.abs(o["u"] - TF["u"]).max() <= tol
     assert np.abs(o["control"] - TF["control_after"]).max() <= tol
-    rel = np.abs(o["state"].T - TF["state_after"]) / np.maximum(np.abs(TF["state_after"]), 1e-3)
-    assert rel.max() <= (1e-4 if precision == 0 else 1e-9)
+    # one Euler step maps a control error du into a pose error <= (v / L) Ts sec^2(delta) du ~ 0.6 du (sbm.py:231-237)
+    assert np.abs(o["state"].T - TF["state_after"]).max() <= (0.6 * QP_TOL if precision == 0 else 1e-9)
 
 
 def test_rollout_one_lap_given_identical_controls(engine_factory):
