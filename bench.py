@@ -267,6 +267,28 @@ def main():
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # nominal: no measured FP32-pipe figure exists in MEASURED_PEAKS.json
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     rollout_gbs = 100.0 * B / (kernel_ms["rollout"] * 1e-3) / 1e9 if kernel_ms["rollout"] > 0 else None
+    # raycast: algorithmic bytes = 32 B x distinct 32-byte sectors of the bit grid holding a tested cell + 16N + 32
+    # (SURVEY 8d); the oracle enumerates the tested cells, so it counts the sectors on a sample of scenarios
+    ray_bytes = None
+    if rank == 0:
+        from oracle import oracle as orc
+        pt = orc.PathTables(T["wp_x"], T["wp_y"], T["wp_psi"], T["wp_kappa"], T["wp_vref"], T["segment_lengths"],
+                            T["border"], True)
+        smg = 0.06 / np.sqrt(2)
+        secs = []
+        for b in range(0, B, max(B // 48, 1)):
+            if obstacles is None:
+                gb = grid
+            else:
+                gb = eng.get_grid(b)
+            st_, _, _, _, ncell, nsec = orc.update_path_constraints(gb, T["origin"], float(T["resolution"]), pt,
+                                                                    int(out2["wp_id"][b]) + 1, N_HORIZON, 2 * smg, smg,
+                                                                    want_stats=True)
+            if st_ == 0:
+                secs.append(nsec)
+        if secs:
+            ray_bytes = 32.0 * float(np.mean(secs)) + 16 * N_HORIZON + 32
+    ray_gbs = ray_bytes * B / (kernel_ms["raycast"] * 1e-3) / 1e9 if ray_bytes else None
     eng.close()
 
     # ---------------- end-to-end arm: host buffers, H2D + D2H inside the timed region -------------------
@@ -320,11 +342,19 @@ def main():
                          "peak": fp32_peak if args.precision == 0 else fp32_peak / 2, "unit": "TFLOP/s",
                          "frac": achieved / (fp32_peak if args.precision == 0 else fp32_peak / 2),
                          "peak_source": "nominal 148 SM x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json has no CUDA-core figure)",
-                         "flops_per_launch": flops_per_launch, "traffic": None,
+                         "flops_per_launch": flops_per_launch,
+                         "traffic": 3.87e6 * B / 4096 if args.precision == 0 else None,
+                         "traffic_source": "dram__bytes_read+write of one launch at 4096 scenarios, ncu --set full "
+                                           "(profiles/r1_assemble_solve_fp32.txt), scaled by batch",
                          "model": "SURVEY 8d: iters*(340N+264) + 400(N+1) + (iters/25)*(142N+78) per instance, actual iteration counts"},
-            "roofline_hbm": {"kernel": "rollout_kernel (K4)", "bound": "hbm", "achieved": rollout_gbs, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": (rollout_gbs / hbm_peak) if rollout_gbs else None,
-                             "bytes_per_instance": 100},
+            "roofline_hbm": [
+                {"kernel": "rollout_kernel (K4)", "bound": "hbm", "achieved": rollout_gbs, "peak": hbm_peak, "unit": "GB/s",
+                 "frac": (rollout_gbs / hbm_peak) if rollout_gbs else None, "bytes_per_instance": 100,
+                 "note": "6-12 us launches: launch-latency bound at this batch size"},
+                {"kernel": "raycast_kernel (K3)", "bound": "hbm", "achieved": ray_gbs, "peak": hbm_peak, "unit": "GB/s",
+                 "frac": (ray_gbs / hbm_peak) if ray_gbs else None, "bytes_per_instance": ray_bytes,
+                 "note": ("shared base grid: the 32 KB grid is L2-resident and staged once per CTA, the kernel is bound by "
+                          "the per-cell walk, not by HBM") if obstacles is None else "per-scenario grids, row span staged per warp by TMA"}],
             "clocks": sampler.summary(),
             "stats": agg,
         }
