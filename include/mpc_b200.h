@@ -167,8 +167,8 @@ int mpc_rollout(mpc_engine *h, double *d_state, const double *d_spatial, const i
 /* ---- fused closed loop on engine-owned scenario state --------------------------------------- *
  * mpc_scenarios_init: allocates B scenarios, copies h_state double[4][B] (x, y, psi, s);
  * controls and infeasibility counters start at zero (MPC.py:53-56).
- * mpc_step: one get_control() + drive(u) for every live scenario (simulation.py:137-140);
- * kernels localise -> raycast -> assemble+solve -> rollout enqueued back to back (CUDA graph).
+ * mpc_step: one get_control() + drive(u) for every live scenario (simulation.py:137-140): two fused
+ * kernels (localise+raycast, assemble+solve+rollout); mpc_run_closed_loop replays them as a CUDA graph.
  * mpc_run_closed_loop: max_steps steps; h_stats double[8] = {scenario-steps, QP solves, ADMM
  * iterations, QP fallbacks, dead scenarios, finished scenarios, sum |e_y|, max |e_y|}. Synchronous. */
 int mpc_scenarios_init(mpc_engine *h, const double *h_state, int32_t B);

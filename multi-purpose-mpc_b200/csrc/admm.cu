@@ -31,10 +31,35 @@ __device__ __forceinline__ void write_solution(int N, int lane, const T w[5], do
     if (lane < N) { xo[3 * (N + 1) + 2 * lane] = (double)w[3]; xo[3 * (N + 1) + 2 * lane + 1] = (double)w[4]; }
 }
 
+// BicycleModel.drive (sbm.py:221-244) fused behind the solve on the closed-loop path.  Explicit round-to-nearest
+// intrinsics: this file is compiled with FMA contraction on, the standalone rollout_kernel without, and both
+// must produce the same bits.
+__device__ __forceinline__ void drive_one(double* __restrict__ state, int b, int B, double e_y, double e_psi,
+                                          double kappa_wp, double v, double delta, double L, double Ts) {
+    const double psi = state[2 * (size_t)B + b];
+    const double x_dot = __dmul_rn(v, cos(psi));                       // sbm.py:231
+    const double y_dot = __dmul_rn(v, sin(psi));                       // sbm.py:232
+    const double psi_dot = __dmul_rn(__ddiv_rn(v, L), tan(delta));     // sbm.py:233
+    state[b] = __dadd_rn(state[b], __dmul_rn(x_dot, Ts));              // sbm.py:237
+    state[(size_t)B + b] = __dadd_rn(state[(size_t)B + b], __dmul_rn(y_dot, Ts));
+    state[2 * (size_t)B + b] = __dadd_rn(psi, __dmul_rn(psi_dot, Ts));
+    const double s_dot = __dmul_rn(__dmul_rn(__ddiv_rn(1.0, __dsub_rn(1.0, __dmul_rn(e_y, kappa_wp))), v), cos(e_psi));  // sbm.py:240
+    state[3 * (size_t)B + b] = __dadd_rn(state[3 * (size_t)B + b], __dmul_rn(s_dot, Ts));  // sbm.py:244
+}
+
+struct RolloutArgs {  // non-null state: fuse the rollout of this scenario behind its solve
+    double* state;
+    const double* spatial;
+    const double* kappa;
+    int wp;
+    double Ts;
+    int B;
+};
+
 template <typename T, typename Comm>
 __device__ __forceinline__ void control_epilogue(Comm& cm, const MpcParams& mp, int lane, const T w[5], const SolveResult& r,
                                                  double* cc, int* infeas, double* u_out, int* iters, int* qp_status,
-                                                 int* flags, int b, int fl) {
+                                                 int* flags, int b, int fl, const RolloutArgs& ro) {
     const int N = mp.N;
     const bool ok = !(r.status == -3 || r.status == -4 || r.status == -7);  // OSQP returns x (MPC.py:185-206)
     int inf = infeas[b];
@@ -59,6 +84,9 @@ __device__ __forceinline__ void control_epilogue(Comm& cm, const MpcParams& mp, 
     }
     if (lane == 0) {
         if (inf == N - 1) fl |= MPC_ST_DEAD;  // MPC.py:218-220
+        if (ro.state && !(fl & MPC_ST_DEAD))
+            drive_one(ro.state, b, ro.B, ro.spatial[b], ro.spatial[(size_t)ro.B + b], ro.kappa[ro.wp],
+                      u_out[2 * (size_t)b], u_out[2 * (size_t)b + 1], mp.L, ro.Ts);
         infeas[b] = inf;
         if (flags) flags[b] = fl;
         if (iters) iters[b] = r.iters;
@@ -99,7 +127,7 @@ assemble_solve_kernel(MpcParams mp, AdmmSettings st, PathView pv, const double* 
                       const int* __restrict__ wp_id, double* __restrict__ control, const double* __restrict__ ub,
                       const double* __restrict__ lb, int* __restrict__ infeas, double* __restrict__ u_out,
                       double* __restrict__ x_out, int* __restrict__ iters, int* __restrict__ qp_status,
-                      int* __restrict__ flags, int B) {
+                      int* __restrict__ flags, int B, double* __restrict__ rollout_state, double Ts) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (b >= B) return;
@@ -116,7 +144,8 @@ assemble_solve_kernel(MpcParams mp, AdmmSettings st, PathView pv, const double* 
     T w[5];
     const SolveResult r = admm_solve<T, NLEV, RLEV>(cm, s, st, lane, N + 1, n, sm, w);
     write_solution<T>(N, lane, w, x_out ? x_out + (size_t)b * n : nullptr);
-    control_epilogue<T>(cm, mp, lane, w, r, cc, infeas, u_out, iters, qp_status, flags, b, fl);
+    const RolloutArgs ro{rollout_state, spatial, pv.kappa, wp_id[b], Ts, B};
+    control_epilogue<T>(cm, mp, lane, w, r, cc, infeas, u_out, iters, qp_status, flags, b, fl, ro);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -151,7 +180,7 @@ assemble_solve_block_kernel(MpcParams mp, AdmmSettings st, PathView pv, const do
                             const int* __restrict__ wp_id, double* __restrict__ control, const double* __restrict__ ub,
                             const double* __restrict__ lb, int* __restrict__ infeas, double* __restrict__ u_out,
                             double* __restrict__ x_out, int* __restrict__ iters, int* __restrict__ qp_status,
-                            int* __restrict__ flags, int B) {
+                            int* __restrict__ flags, int B, double* __restrict__ rollout_state, double Ts) {
     const int lane = threadIdx.x, b = blockIdx.x;
     if (b >= B) return;
     const int fl = flags ? flags[b] : 0;
@@ -167,7 +196,8 @@ assemble_solve_block_kernel(MpcParams mp, AdmmSettings st, PathView pv, const do
     T w[5];
     const SolveResult r = admm_solve<T, NLEV, 0>(cm, s, st, lane, N + 1, n, sm, w);
     write_solution<T>(N, lane, w, x_out ? x_out + (size_t)b * n : nullptr);
-    control_epilogue<T>(cm, mp, lane, w, r, cc, infeas, u_out, iters, qp_status, flags, b, fl);
+    const RolloutArgs ro{rollout_state, spatial, pv.kappa, wp_id[b], Ts, B};
+    control_epilogue<T>(cm, mp, lane, w, r, cc, infeas, u_out, iters, qp_status, flags, b, fl, ro);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -188,13 +218,13 @@ template <typename T, int NLEV, int RLEV, int MINB>
 static void assemble_solve_launch(const MpcParams& mp, const AdmmSettings& st, const PathView& pv, const double* spatial,
                                   const int* wp_id, double* control, const double* ub, const double* lb, int* infeas,
                                   double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
-                                  cudaStream_t s) {
+                                  cudaStream_t s, double* rs, double Ts) {
     constexpr int R = clamp_rlev<NLEV, RLEV>();
     const int grid = (B + kWarpsPerBlock - 1) / kWarpsPerBlock, block = 32 * kWarpsPerBlock;
     const size_t smem = warp_smem_bytes<T, NLEV, R>();
     cudaFuncSetAttribute(assemble_solve_kernel<T, NLEV, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     assemble_solve_kernel<T, NLEV, R, MINB><<<grid, block, smem, s>>>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas,
-                                                                      u_out, x_out, iters, qp_status, flags, B);
+                                                                      u_out, x_out, iters, qp_status, flags, B, rs, Ts);
 }
 
 template <typename T, int NLEV, int NT>
@@ -210,11 +240,11 @@ template <typename T, int NLEV, int NT>
 static void assemble_solve_block_launch(const MpcParams& mp, const AdmmSettings& st, const PathView& pv,
                                         const double* spatial, const int* wp_id, double* control, const double* ub,
                                         const double* lb, int* infeas, double* u_out, double* x_out, int* iters,
-                                        int* qp_status, int* flags, int B, cudaStream_t s) {
+                                        int* qp_status, int* flags, int B, cudaStream_t s, double* rs, double Ts) {
     const size_t smem = block_smem_bytes<T, NLEV, NT>();
     cudaFuncSetAttribute(assemble_solve_block_kernel<T, NLEV, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     assemble_solve_block_kernel<T, NLEV, NT><<<B, NT, smem, s>>>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out,
-                                                                x_out, iters, qp_status, flags, B);
+                                                                x_out, iters, qp_status, flags, B, rs, Ts);
 }
 
 int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax,
@@ -238,9 +268,9 @@ int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* 
 int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings& st, const PathView& pv,
                           const double* spatial, const int* wp_id, double* control, const double* ub, const double* lb,
                           int* infeas, double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
-                          cudaStream_t s) {
-#define WARP_GO(T_, L_) assemble_solve_launch<T_, L_, Tune<T_>::rlev, Tune<T_>::minb>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s)
-#define BLOCK_GO(T_, L_, NT_) assemble_solve_block_launch<T_, L_, NT_>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s)
+                          cudaStream_t s, double* rollout_state, double Ts) {
+#define WARP_GO(T_, L_) assemble_solve_launch<T_, L_, Tune<T_>::rlev, Tune<T_>::minb>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts)
+#define BLOCK_GO(T_, L_, NT_) assemble_solve_block_launch<T_, L_, NT_>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts)
     const int ns = mp.N + 1;
     if (ns > 128) return MPC_E_UNSUPPORTED;
     if (precision == 1) {

@@ -495,28 +495,44 @@ int mpc_scenarios_set_state(mpc_engine* h, const double* h_state, const double* 
     return 0;
 }
 
-// the four kernels of one closed-loop step (simulation.py:137-140), optionally bracketed by events
+// One closed-loop step (simulation.py:137-140).  Fused path (default): two kernels -- K4a+K3 (localise inside the
+// raycast kernel) and K1+K2+K4b (rollout behind the solve).  Profiling path: the four kernels of the ABI, bracketed by
+// events, so that each gets its own duration.
 static int enqueue_step(mpc_engine* h, bool with_stats, bool timed) {
     const int B = h->B;
     cudaStream_t s = h->stream;
-    if (timed) cudaEventRecord(h->ev[0], s);
-    launch_localize(h->s_state.p, h->s_wp_id.p, h->s_spatial.p, h->s_flags.p, h->pv, h->length, B, s);
-    if (timed) cudaEventRecord(h->ev[1], s);
     const double sm = h->cfg.car_width / std::sqrt(2.0);
     const uint32_t* grids = h->grids_B ? h->d_grids.p : h->d_base.p;
     const size_t stride = h->grids_B ? (size_t)h->words : 0;
+    if (!timed) {
+        launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm,
+                       h->s_ub.p, h->s_lb.p, nullptr, h->s_flags.p, B, h->rowspan_valid, s, h->s_state.p, h->s_wp_id.p,
+                       h->s_spatial.p, h->length);
+        int r = launch_assemble_solve(h->cfg.precision, h->mp, h->st, h->pv, h->s_spatial.p, h->s_wp_id.p, h->s_control.p,
+                                      h->s_ub.p, h->s_lb.p, h->s_infeas.p, h->s_u.p, nullptr, h->s_iters.p,
+                                      h->s_qp_status.p, h->s_flags.p, B, s, h->s_state.p, h->cfg.Ts);
+        if (r) return fail(r, "unsupported horizon");
+        // the rollout only touches `state`; flags / iters / e_y of this step are final, so the statistics can follow it
+        if (with_stats) launch_accumulate_stats(h->s_flags.p, h->s_iters.p, h->s_spatial.p, h->s_acc.p, B, s);
+        h->launches += with_stats ? 3 : 2;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    cudaEventRecord(h->ev[0], s);
+    launch_localize(h->s_state.p, h->s_wp_id.p, h->s_spatial.p, h->s_flags.p, h->pv, h->length, B, s);
+    cudaEventRecord(h->ev[1], s);
     launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm,
                    h->s_ub.p, h->s_lb.p, nullptr, h->s_flags.p, B, h->rowspan_valid, s);
-    if (timed) cudaEventRecord(h->ev[2], s);
+    cudaEventRecord(h->ev[2], s);
     int r = launch_assemble_solve(h->cfg.precision, h->mp, h->st, h->pv, h->s_spatial.p, h->s_wp_id.p, h->s_control.p,
                                   h->s_ub.p, h->s_lb.p, h->s_infeas.p, h->s_u.p, nullptr, h->s_iters.p,
                                   h->s_qp_status.p, h->s_flags.p, B, s);
     if (r) return fail(r, "unsupported horizon");
-    if (timed) cudaEventRecord(h->ev[3], s);
+    cudaEventRecord(h->ev[3], s);
     if (with_stats) launch_accumulate_stats(h->s_flags.p, h->s_iters.p, h->s_spatial.p, h->s_acc.p, B, s);
     launch_rollout(h->s_state.p, h->s_spatial.p, h->s_wp_id.p, h->s_u.p, h->s_flags.p, h->pv, h->cfg.car_length,
                    h->cfg.Ts, B, s);
-    if (timed) cudaEventRecord(h->ev[4], s);
+    cudaEventRecord(h->ev[4], s);
     h->launches += with_stats ? 5 : 4;
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -605,7 +621,7 @@ int mpc_run_closed_loop(mpc_engine* h, int32_t max_steps, double* h_stats) {
     } else {
         if (int r = ensure_graph(h)) return r;
         for (int k = 0; k < max_steps; ++k) CUDA_OK(cudaGraphLaunch(h->graph_exec, h->stream));
-        h->launches += 5 * (int64_t)max_steps;
+        h->launches += 3 * (int64_t)max_steps;
     }
     if (h_stats) {
         DevBuf<double> out;

@@ -23,7 +23,8 @@ int raycast_plan(const GridView& g, int N, bool shared_grid, int max_rows, bool 
 void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridView& g, const PathView& pv,
                     const int2* rowspan, int max_rows, const int* wp_id, int first_offset, int N, double min_width,
                     double sm, double* ub, double* lb, double* cells_sm, int* flags, int B, bool rowspan_ok,
-                    cudaStream_t st);
+                    cudaStream_t st, const double* state = nullptr, int* wp_id_out = nullptr,
+                    double* spatial_out = nullptr, double length = 0.0);
 void launch_localize(const double* state, int* wp_id, double* spatial, int* flags, const PathView& pv, double length,
                      int B, cudaStream_t st);
 void launch_rollout(double* state, const double* spatial, const int* wp_id, const double* u, const int* flags,
@@ -37,6 +38,6 @@ int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* 
 int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings& st, const PathView& pv,
                           const double* spatial, const int* wp_id, double* control, const double* ub, const double* lb,
                           int* infeas, double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
-                          cudaStream_t s);
+                          cudaStream_t s, double* rollout_state = nullptr, double Ts = 0.0);
 
 }  // namespace mpcb

@@ -148,6 +148,46 @@ void launch_compute_width(const uint32_t* grid, const GridView& g, const PathVie
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4 front: SpatialBicycleModel.get_current_waypoint + t2s (sbm.py:256-279, 183-219)
+// ------------------------------------------------------------------------------------------------
+// returns the waypoint index, or -1 when s is past the end of the path (simulation.py:134 loop condition)
+__device__ __forceinline__ int localize_one(const double* __restrict__ state, double* __restrict__ spatial,
+                                            const PathView& pv, double length, int b, int B) {
+    const double x = state[b], y = state[(size_t)B + b], psi = state[2 * (size_t)B + b], s = state[3 * (size_t)B + b];
+    // first index with length_cum > s  (sbm.py:265-266); all-False -> IndexError in the reference
+    int lo = 0, hi = pv.n_wp;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pv.length_cum[mid] > s) hi = mid; else lo = mid + 1;
+    }
+    if (lo >= pv.n_wp || !(s < length)) return -1;
+    const int next = lo, prev = next > 0 ? next - 1 : pv.n_wp - 1;  // index -1 wraps in numpy
+    const double s_next = pv.length_cum[next], s_prev = pv.length_cum[prev];
+    const int w = (fabs(s - s_next) < fabs(s - s_prev)) ? next : prev;  // strict <: ties -> prev (quirk Q8)
+    const double e_y = pv.cos_psi[w] * (y - pv.y[w]) - pv.sin_psi[w] * (x - pv.x[w]);  // sbm.py:202-205
+    const double PI = 3.141592653589793;
+    double e_psi = psi - pv.psi[w];
+    e_psi = np_mod(e_psi + PI, 2 * PI) - PI;  // sbm.py:209
+    spatial[b] = e_y;
+    spatial[(size_t)B + b] = e_psi;
+    return w;
+}
+
+__global__ void localize_t2s_kernel(const double* __restrict__ state, int* __restrict__ wp_id,
+                                    double* __restrict__ spatial, int* __restrict__ flags, PathView pv, double length,
+                                    int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (flags && (flags[b] & (MPC_ST_DEAD | MPC_ST_FINISHED))) return;
+    const int w = localize_one(state, spatial, pv, length, b, B);
+    if (w < 0) {
+        if (flags) atomicOr(&flags[b], MPC_ST_FINISHED);
+        return;
+    }
+    wp_id[b] = w;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: ReferencePath.update_path_constraints (rp.py:522-648) on per-scenario bit-packed grids.
 // One warp per scenario.  The rows of the grid that the horizon's rays can touch are one
 // contiguous byte range (full 64 B-pitch rows): a single cp.async.bulk (TMA bulk copy, UBLKCP)
@@ -212,6 +252,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
 
 // Walk the anti-aliased ray of one horizon waypoint over a bit grid and record its free segments
 // (rp.py:466-520).  bits(row, word) returns the 32-bit word of the grid.
+// The line walk emits up to three cells per step of the main chain (the chain cell and two anti-aliasing side
+// cells, in skimage's order); the three visits are PREDICATED rather than branched so that the 30 lanes of a
+// warp, which walk rays of different slopes, stay converged.  Only closing a free segment (rare) branches.
 template <typename Bits>
 __device__ __forceinline__ int walk_free_segments(const GridView& g, const double* bc, double min_width, short4* segs,
                                                   int& bad, Bits&& bits) {
@@ -221,28 +264,32 @@ __device__ __forceinline__ int walk_free_segments(const GridView& g, const doubl
     // every emitted cell lies within one pixel of the segment's bounding box
     const bool inside = min(ubx, lbx) >= 1 && min(uby, lby) >= 1 && max(ubx, lbx) < g.W - 1 && max(uby, lby) < g.H - 1;
     int uo_x = ubx, uo_y = uby, free_cells = 0, nseg = 0;
-    auto visit = [&](int x, int y) {
+    auto close_segment = [&](int x, int y) {
+        double ux, uy, lx, ly;
+        m2w(g, uo_x, uo_y, ux, uy);
+        m2w(g, x, y, lx, ly);
+        if (sqrt(sq(ux - lx) + sq(uy - ly)) > min_width) {  // rp.py:510
+            if (nseg < kMaxSeg) segs[nseg] = make_short4((short)uo_x, (short)uo_y, (short)x, (short)y);
+            ++nseg;
+        }
+    };
+    auto visit = [&](int x, int y, bool active) {
         int xx = x, yy = y;
         if (!inside) {  // numpy index semantics: negative wraps once, anything else is an IndexError
             xx = x < 0 ? x + g.W : x; yy = y < 0 ? y + g.H : y;
-            if (xx < 0 || yy < 0 || xx >= g.W || yy >= g.H) { bad = 1; return; }
+            if (xx < 0 || yy < 0 || xx >= g.W || yy >= g.H) { bad |= active; xx = 0; yy = 0; active = false; }
         }
         const int v = (bits(yy, xx >> 5) >> (xx & 31)) & 1u;
-        free_cells |= v;
+        free_cells |= (v & (int)active);
         const bool at_end = (x == lbx) & (y == lby);
-        if ((!v | at_end) & free_cells) {
-            double ux, uy, lx, ly;
-            m2w(g, uo_x, uo_y, ux, uy);
-            m2w(g, x, y, lx, ly);
-            if (sqrt(sq(ux - lx) + sq(uy - ly)) > min_width) {  // rp.py:510
-                if (nseg < kMaxSeg) segs[nseg] = make_short4((short)uo_x, (short)uo_y, (short)x, (short)y);
-                ++nseg;
-            }
-            uo_x = x; uo_y = y;
+        const bool closing = active & ((!v) | at_end) & (free_cells != 0);
+        if (closing) {  // rp.py:503-515
+            close_segment(x, y);
             free_cells = 0;
-        } else if (!v) {  // occupied and no free run open (rp.py:516-518)
-            uo_x = x; uo_y = y;
         }
+        const bool move_uo = active & ((!v) | closing);  // rp.py:514 / 516-518
+        uo_x = move_uo ? x : uo_x;
+        uo_y = move_uo ? y : uo_y;
     };
     // skimage.draw.line_aa(x0, y0, x1, y1): r = x, c = y; the first emitted cell is skipped (rp.py:494, Q4)
     const int r0 = ubx, c0 = uby, r1 = lbx, c1 = lby;
@@ -254,22 +301,20 @@ __device__ __forceinline__ int walk_free_segments(const GridView& g, const doubl
     int c = c0, r = r0;
     bool first = true;
     for (;;) {
-        if (!first) visit(r, c);
+        visit(r, c, !first);
         first = false;
         const float e0 = err;
         const int c_prev = c;
-        if (2 * e0 >= -fdc) {
-            if (c == c1) break;
-            if (e0 + fdr < ed) visit(r + sign_r, c);
-            err -= fdr;
-            c += sign_c;
-        }
-        if (2 * e0 <= fdr) {
-            if (r == r1) break;
-            if (fdc - e0 < ed) visit(r, c_prev + sign_c);
-            err += fdc;
-            r += sign_r;
-        }
+        const bool step_c = 2 * e0 >= -fdc;
+        if (step_c & (c == c1)) break;
+        visit(r + sign_r, c, step_c & (e0 + fdr < ed));
+        err -= step_c ? fdr : 0.0f;
+        c += step_c ? sign_c : 0;
+        const bool step_r = 2 * e0 <= fdr;
+        if (step_r & (r == r1)) break;
+        visit(r, c_prev + sign_c, step_r & (fdc - e0 < ed));
+        err += step_r ? fdc : 0.0f;
+        r += step_r ? sign_r : 0;
     }
     return nseg;
 }
@@ -287,6 +332,11 @@ struct RaycastArgs {
     int* flags;
     int B;
     int stage_rows;  // rows of shared memory reserved per staging slab (0: read the grid from global memory)
+    // fused K4a (closed-loop path): when state != nullptr lane 0 first localises the car and writes wp_id / spatial
+    const double* state;
+    int* wp_id_out;
+    double* spatial_out;
+    double length;
 };
 
 // MODE 0: no staging (global / L1 reads).  MODE 1: one grid shared by all scenarios, staged once per CTA
@@ -326,7 +376,21 @@ raycast_kernel(RaycastArgs a) {
     for (int b = blockIdx.x * nwarps + warp; b < a.B; b += gridDim.x * nwarps) {
         const int fl = a.flags ? a.flags[b] : 0;
         if (fl & (MPC_ST_DEAD | MPC_ST_FINISHED)) continue;
-        const long first = (long)a.wp_id[b] + a.first_offset;
+        int wp_now;
+        if (a.state) {  // get_current_waypoint + t2s (sbm.py:256-279, 183-219), same arithmetic as localize_t2s_kernel
+            int w = -1;
+            if (lane == 0) w = localize_one(a.state, a.spatial_out, pv, a.length, b, a.B);
+            w = __shfl_sync(0xffffffffu, w, 0);
+            if (w < 0) {
+                if (lane == 0 && a.flags) atomicOr(&a.flags[b], MPC_ST_FINISHED);
+                continue;
+            }
+            if (lane == 0) a.wp_id_out[b] = w;
+            wp_now = w;
+        } else {
+            wp_now = a.wp_id[b];
+        }
+        const long first = (long)wp_now + a.first_offset;
         int status = 0;
         if (!pv.circular && first + N - 1 >= pv.n_wp) status |= MPC_ST_END_OF_PATH;  // rp.py:367-369
         const int first_w = (int)(first % pv.n_wp);
@@ -479,8 +543,9 @@ int raycast_plan(const GridView& g, int N, bool shared_grid, int max_rows, bool 
 void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridView& g, const PathView& pv,
                     const int2* rowspan, int max_rows, const int* wp_id, int first_offset, int N, double min_width,
                     double sm, double* ub, double* lb, double* cells_sm, int* flags, int B, bool rowspan_ok,
-                    cudaStream_t st) {
+                    cudaStream_t st, const double* state, int* wp_id_out, double* spatial_out, double length) {
     RaycastArgs a;
+    a.state = state; a.wp_id_out = wp_id_out; a.spatial_out = spatial_out; a.length = length;
     a.grids = grids; a.grid_stride_words = grid_stride_words; a.g = g; a.pv = pv; a.rowspan = rowspan; a.wp_id = wp_id;
     a.first_offset = first_offset; a.N = N; a.min_width = min_width; a.sm = sm; a.ub_out = ub; a.lb_out = lb;
     a.cells_sm_out = cells_sm; a.flags = flags; a.B = B;
@@ -507,35 +572,6 @@ void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridV
 // ------------------------------------------------------------------------------------------------
 // K4 front: SpatialBicycleModel.get_current_waypoint + t2s (sbm.py:256-279, 183-219)
 // ------------------------------------------------------------------------------------------------
-__global__ void localize_t2s_kernel(const double* __restrict__ state, int* __restrict__ wp_id,
-                                    double* __restrict__ spatial, int* __restrict__ flags, PathView pv, double length,
-                                    int B) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    if (flags && (flags[b] & (MPC_ST_DEAD | MPC_ST_FINISHED))) return;
-    const double x = state[b], y = state[(size_t)B + b], psi = state[2 * (size_t)B + b], s = state[3 * (size_t)B + b];
-    // first index with length_cum > s  (sbm.py:265-266); all-False -> IndexError in the reference
-    int lo = 0, hi = pv.n_wp;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (pv.length_cum[mid] > s) hi = mid; else lo = mid + 1;
-    }
-    if (lo >= pv.n_wp || !(s < length)) {  // simulation.py:134 loop condition
-        if (flags) atomicOr(&flags[b], MPC_ST_FINISHED);
-        return;
-    }
-    const int next = lo, prev = next > 0 ? next - 1 : pv.n_wp - 1;  // index -1 wraps in numpy
-    const double s_next = pv.length_cum[next], s_prev = pv.length_cum[prev];
-    const int w = (fabs(s - s_next) < fabs(s - s_prev)) ? next : prev;  // strict <: ties -> prev (quirk Q8)
-    wp_id[b] = w;
-    const double e_y = pv.cos_psi[w] * (y - pv.y[w]) - pv.sin_psi[w] * (x - pv.x[w]);  // sbm.py:202-205
-    const double PI = 3.141592653589793;
-    double e_psi = psi - pv.psi[w];
-    e_psi = np_mod(e_psi + PI, 2 * PI) - PI;  // sbm.py:209
-    spatial[b] = e_y;
-    spatial[(size_t)B + b] = e_psi;
-}
-
 void launch_localize(const double* state, int* wp_id, double* spatial, int* flags, const PathView& pv, double length,
                      int B, cudaStream_t st) {
     localize_t2s_kernel<<<(B + 255) / 256, 256, 0, st>>>(state, wp_id, spatial, flags, pv, length, B);
