@@ -60,6 +60,9 @@ struct mpc_engine {
     int grids_B = 0;  // 0: shared base grid
     bool have_grid = false;
     DevBuf<int2> d_rowspan;
+    DevBuf<uint32_t> d_ray_cells;  // ray table [max_len][n_wp] (geometry.cu)
+    DevBuf<int> d_ray_len;
+    int ray_max_len = 0;
     bool rowspan_valid = false;
     int max_rows = 0;
     DevBuf<int> d_err;
@@ -156,7 +159,7 @@ int mpc_engine_destroy(mpc_engine* h) {
     cudaStreamSynchronize(h->stream);
     drop_graph(h);
     h->d_wp.release(); h->d_border.release(); h->d_base.release(); h->d_grids.release(); h->d_obs_px.release();
-    h->d_obs_off.release(); h->d_rowspan.release(); h->d_err.release();
+    h->d_obs_off.release(); h->d_rowspan.release(); h->d_err.release(); h->d_ray_cells.release(); h->d_ray_len.release();
     h->s_state.release(); h->s_spatial.release(); h->s_control.release(); h->s_ub.release(); h->s_lb.release();
     h->s_u.release(); h->s_acc.release(); h->s_wp_id.release(); h->s_iters.release(); h->s_qp_status.release();
     h->s_flags.release(); h->s_infeas.release();
@@ -233,8 +236,24 @@ static int compute_rowspan(mpc_engine* h) {
     CUDA_OK(h->d_rowspan.alloc(n));
     CUDA_OK(cudaMemcpyAsync(h->d_rowspan.p, rs.data(), n * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
-    h->rowspan_valid = true;
     h->max_rows = max_rows;
+    // ray table: one entry per emitted cell of every waypoint's ray; 3 cells per chain step bounds the length
+    int max_len = 0;
+    for (int k = 0; k < n; ++k) {
+        const double* b = &h->h_border[4 * k];
+        const long dx = std::labs((long)std::floor((b[0] - h->g.ox) / h->g.res) - (long)std::floor((b[2] - h->g.ox) / h->g.res));
+        const long dy = std::labs((long)std::floor((b[1] - h->g.oy) / h->g.res) - (long)std::floor((b[3] - h->g.oy) / h->g.res));
+        max_len = std::max(max_len, (int)std::min<long>(3 * (dx + dy) + 4, 1 << 20));
+    }
+    if ((size_t)h->words >= (1u << 21)) return fail(MPC_E_UNSUPPORTED, "grid too large for the packed ray table");
+    h->ray_max_len = max_len;
+    CUDA_OK(h->d_ray_cells.alloc((size_t)max_len * n));
+    CUDA_OK(h->d_ray_len.alloc(n));
+    launch_build_ray_table(h->g, h->pv, h->d_ray_cells.p, h->d_ray_len.p, max_len, h->stream);
+    ++h->launches;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->rowspan_valid = true;
     return 0;
 }
 
@@ -394,7 +413,8 @@ int mpc_update_path_constraints(mpc_engine* h, const int32_t* d_wp_id, int32_t f
     const size_t stride = h->grids_B ? (size_t)h->words : 0;
     // the row-span table is built for the engine's own horizon (first waypoint wp_id+1, N = cfg.N)
     const bool rowspan_ok = h->rowspan_valid && N == h->cfg.N && first_offset == 1;
-    launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, d_wp_id, first_offset, N, min_width,
+    if (!h->rowspan_valid) return fail(MPC_E_STATE, "ray table not built (path, border cells and grid are all required)");
+    launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->d_ray_cells.p, h->d_ray_len.p, d_wp_id, first_offset, N, min_width,
                    safety_margin, d_ub, d_lb, d_cells_sm, d_flags, B, rowspan_ok, h->stream);
     ++h->launches;
     CUDA_OK(cudaGetLastError());
@@ -505,7 +525,7 @@ static int enqueue_step(mpc_engine* h, bool with_stats, bool timed) {
     const uint32_t* grids = h->grids_B ? h->d_grids.p : h->d_base.p;
     const size_t stride = h->grids_B ? (size_t)h->words : 0;
     if (!timed) {
-        launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm,
+        launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->d_ray_cells.p, h->d_ray_len.p, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm,
                        h->s_ub.p, h->s_lb.p, nullptr, h->s_flags.p, B, h->rowspan_valid, s, h->s_state.p, h->s_wp_id.p,
                        h->s_spatial.p, h->length);
         int r = launch_assemble_solve(h->cfg.precision, h->mp, h->st, h->pv, h->s_spatial.p, h->s_wp_id.p, h->s_control.p,
@@ -521,7 +541,7 @@ static int enqueue_step(mpc_engine* h, bool with_stats, bool timed) {
     cudaEventRecord(h->ev[0], s);
     launch_localize(h->s_state.p, h->s_wp_id.p, h->s_spatial.p, h->s_flags.p, h->pv, h->length, B, s);
     cudaEventRecord(h->ev[1], s);
-    launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm,
+    launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->d_ray_cells.p, h->d_ray_len.p, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm,
                    h->s_ub.p, h->s_lb.p, nullptr, h->s_flags.p, B, h->rowspan_valid, s);
     cudaEventRecord(h->ev[2], s);
     int r = launch_assemble_solve(h->cfg.precision, h->mp, h->st, h->pv, h->s_spatial.p, h->s_wp_id.p, h->s_control.p,

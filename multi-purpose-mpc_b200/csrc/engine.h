@@ -20,8 +20,10 @@ void launch_compute_width(const uint32_t* grid, const GridView& g, const PathVie
                           double* lb, double* border, int* err, cudaStream_t st);
 int raycast_plan(const GridView& g, int N, bool shared_grid, int max_rows, bool rowspan_ok, int* warps, int* stage_rows,
                  size_t* smem);
+void launch_build_ray_table(const GridView& g, const PathView& pv, uint32_t* cells, int* len, int max_len,
+                            cudaStream_t st);
 void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridView& g, const PathView& pv,
-                    const int2* rowspan, int max_rows, const int* wp_id, int first_offset, int N, double min_width,
+                    const int2* rowspan, int max_rows, const uint32_t* ray_cells, const int* ray_len, const int* wp_id, int first_offset, int N, double min_width,
                     double sm, double* ub, double* lb, double* cells_sm, int* flags, int B, bool rowspan_ok,
                     cudaStream_t st, const double* state = nullptr, int* wp_id_out = nullptr,
                     double* spatial_out = nullptr, double length = 0.0);

@@ -250,44 +250,45 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
     }
 }
 
+// closing a free segment (rp.py:503-515) is rare: keep its fp64 arithmetic out of line so that the three visit
+// sites of the walk stay small
+__device__ __noinline__ int close_segment(double ox, double oy, double res, int uo_x, int uo_y, int x, int y,
+                                          double min_width, short4* segs, int nseg) {
+    const double ux = ((double)uo_x + 0.5) * res + ox, uy = ((double)uo_y + 0.5) * res + oy;  // map.py:98-99
+    const double lx = ((double)x + 0.5) * res + ox, ly = ((double)y + 0.5) * res + oy;
+    if (sqrt(sq(ux - lx) + sq(uy - ly)) > min_width) {  // rp.py:510
+        if (nseg < kMaxSeg) segs[nseg] = make_short4((short)uo_x, (short)uo_y, (short)x, (short)y);
+        ++nseg;
+    }
+    return nseg;
+}
+
 // Walk the anti-aliased ray of one horizon waypoint over a bit grid and record its free segments
-// (rp.py:466-520).  bits(row, word) returns the 32-bit word of the grid.
+// (rp.py:466-520).  `base[y * pitch + (x >> 5)]` is the grid word of cell (x, y).
 // The line walk emits up to three cells per step of the main chain (the chain cell and two anti-aliasing side
 // cells, in skimage's order); the three visits are PREDICATED rather than branched so that the 30 lanes of a
 // warp, which walk rays of different slopes, stay converged.  Only closing a free segment (rare) branches.
-template <typename Bits>
-__device__ __forceinline__ int walk_free_segments(const GridView& g, const double* bc, double min_width, short4* segs,
-                                                  int& bad, Bits&& bits) {
-    int ubx, uby, lbx, lby;
-    w2m(g, bc[0], bc[1], ubx, uby);  // rp.py:478
-    w2m(g, bc[2], bc[3], lbx, lby);  // rp.py:480
-    // every emitted cell lies within one pixel of the segment's bounding box
-    const bool inside = min(ubx, lbx) >= 1 && min(uby, lby) >= 1 && max(ubx, lbx) < g.W - 1 && max(uby, lby) < g.H - 1;
+// INSIDE = every emitted cell is known to be inside the grid (the usual case): no per-cell bounds checks.
+template <bool INSIDE>
+__device__ __forceinline__ int walk_ray(const uint32_t* __restrict__ base, int pitch, int W, int H, double ox, double oy,
+                                        double res, int ubx, int uby, int lbx, int lby, double min_width, short4* segs,
+                                        int& bad) {
     int uo_x = ubx, uo_y = uby, free_cells = 0, nseg = 0;
-    auto close_segment = [&](int x, int y) {
-        double ux, uy, lx, ly;
-        m2w(g, uo_x, uo_y, ux, uy);
-        m2w(g, x, y, lx, ly);
-        if (sqrt(sq(ux - lx) + sq(uy - ly)) > min_width) {  // rp.py:510
-            if (nseg < kMaxSeg) segs[nseg] = make_short4((short)uo_x, (short)uo_y, (short)x, (short)y);
-            ++nseg;
-        }
-    };
     auto visit = [&](int x, int y, bool active) {
         int xx = x, yy = y;
-        if (!inside) {  // numpy index semantics: negative wraps once, anything else is an IndexError
-            xx = x < 0 ? x + g.W : x; yy = y < 0 ? y + g.H : y;
-            if (xx < 0 || yy < 0 || xx >= g.W || yy >= g.H) { bad |= active; xx = 0; yy = 0; active = false; }
+        if (!INSIDE) {  // numpy index semantics: negative wraps once, anything else is an IndexError
+            xx = x < 0 ? x + W : x; yy = y < 0 ? y + H : y;
+            if (xx < 0 || yy < 0 || xx >= W || yy >= H) { bad |= active; xx = 0; yy = 0; active = false; }
         }
-        const int v = (bits(yy, xx >> 5) >> (xx & 31)) & 1u;
-        free_cells |= (v & (int)active);
+        const uint32_t v = (base[yy * pitch + (xx >> 5)] >> (xx & 31)) & 1u;
+        free_cells |= (int)v & (int)active;
         const bool at_end = (x == lbx) & (y == lby);
-        const bool closing = active & ((!v) | at_end) & (free_cells != 0);
-        if (closing) {  // rp.py:503-515
-            close_segment(x, y);
+        const bool closing = active & ((v == 0) | at_end) & (free_cells != 0);
+        if (closing) {
+            nseg = close_segment(ox, oy, res, uo_x, uo_y, x, y, min_width, segs, nseg);
             free_cells = 0;
         }
-        const bool move_uo = active & ((!v) | closing);  // rp.py:514 / 516-518
+        const bool move_uo = active & ((v == 0) | closing);  // rp.py:514 / 516-518
         uo_x = move_uo ? x : uo_x;
         uo_y = move_uo ? y : uo_y;
     };
@@ -319,12 +320,100 @@ __device__ __forceinline__ int walk_free_segments(const GridView& g, const doubl
     return nseg;
 }
 
+__device__ __forceinline__ int walk_free_segments(const GridView& g, const double* bc, double min_width, short4* segs,
+                                                  int& bad, const uint32_t* __restrict__ base) {
+    int ubx, uby, lbx, lby;
+    w2m(g, bc[0], bc[1], ubx, uby);  // rp.py:478
+    w2m(g, bc[2], bc[3], lbx, lby);  // rp.py:480
+    // every emitted cell lies within one pixel of the segment's bounding box
+    const bool inside = min(ubx, lbx) >= 1 && min(uby, lby) >= 1 && max(ubx, lbx) < g.W - 1 && max(uby, lby) < g.H - 1;
+    if (inside) return walk_ray<true>(base, g.pitch_words, g.W, g.H, g.ox, g.oy, g.res, ubx, uby, lbx, lby, min_width, segs, bad);
+    return walk_ray<false>(base, g.pitch_words, g.W, g.H, g.ox, g.oy, g.res, ubx, uby, lbx, lby, min_width, segs, bad);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ray table: the cell sequence of every waypoint's ray (static border cell -> static border cell) is a
+// property of the path and the grid geometry, not of the scenario.  It is built once (per set_path /
+// set_base_grid / compute_width) by walking skimage's line_aa order on the device, and the per-step kernel
+// replays it: entry = word offset in the grid (bits 5..25) | bit (0..4) | at-end flag (bit 26), layout
+// [cell][waypoint] so that the lanes of a warp (consecutive waypoints) read consecutive words.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kRayEnd = 1u << 26;
+
+__global__ void build_ray_table_kernel(GridView g, PathView pv, uint32_t* __restrict__ cells, int* __restrict__ len,
+                                       int max_len) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= pv.n_wp) return;
+    const double* bc = pv.border + 4 * k;
+    int ubx, uby, lbx, lby;
+    w2m(g, bc[0], bc[1], ubx, uby);  // rp.py:478
+    w2m(g, bc[2], bc[3], lbx, lby);  // rp.py:480
+    int n = 0, bad = 0, first = 1;
+    line_aa_walk(ubx, uby, lbx, lby, [&](int x, int y) {
+        if (first) { first = 0; return true; }  // rp.py:494 skips the first emitted cell (quirk Q4)
+        if (x < 0 || y < 0 || x >= g.W || y >= g.H || n >= max_len) { bad = 1; return false; }
+        const uint32_t word = (uint32_t)(y * g.pitch_words + (x >> 5));
+        cells[(size_t)n * pv.n_wp + k] = (word << 5) | (uint32_t)(x & 31) | ((x == lbx && y == lby) ? kRayEnd : 0u);
+        ++n;
+        return true;
+    });
+    len[k] = bad ? -1 : n;  // -1: the ray leaves the grid (IndexError in the reference, rp.py:496)
+}
+
+void launch_build_ray_table(const GridView& g, const PathView& pv, uint32_t* cells, int* len, int max_len,
+                            cudaStream_t st) {
+    build_ray_table_kernel<<<(pv.n_wp + 127) / 128, 128, 0, st>>>(g, pv, cells, len, max_len);
+}
+
+// Replay one waypoint's ray over a bit grid and record its free segments (rp.py:494-518).
+// base[word] is the grid word (staged rows: base is pre-offset by the first staged row).
+__device__ __forceinline__ int replay_ray(const uint32_t* __restrict__ base, const uint32_t* __restrict__ cells, int n_wp,
+                                          int k, int len, int max_len_warp, int ubx, int uby, int pitch, double ox,
+                                          double oy, double res, double min_width, short4* segs, uint32_t safe_word) {
+    uint32_t uo = 0xffffffffu;  // packed cell of the segment's upper end; all ones = the ray's start cell
+    int free_cells = 0, nseg = 0;
+    const uint32_t* p = cells + k;
+    const uint32_t safe = safe_word << 5;  // predicated-off slots still load a grid word: keep it inside the staged rows
+    constexpr int U = 8;
+    // all lanes run the warp's longest ray so that the loads stay converged; shorter rays are predicated off.
+    // U table entries and their grid words are fetched ahead of the (serial) segment state machine.
+    for (int i0 = 0; i0 < max_len_warp; i0 += U, p += (size_t)U * n_wp) {
+        uint32_t e[U], wv[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) e[j] = (i0 + j < len) ? __ldg(p + (size_t)j * n_wp) : safe;
+#pragma unroll
+        for (int j = 0; j < U; ++j) wv[j] = base[(e[j] >> 5) & 0x1fffffu];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const bool active = i0 + j < len;
+            const uint32_t v = (wv[j] >> (e[j] & 31u)) & 1u;
+            free_cells |= (int)v & (int)active;
+            const bool closing = active & ((v == 0u) | ((e[j] & kRayEnd) != 0u)) & (free_cells != 0);
+            if (closing) {  // rp.py:503-515
+                const uint32_t w = (e[j] >> 5) & 0x1fffffu;
+                const int y = (int)(w / (uint32_t)pitch), x = (int)(w % (uint32_t)pitch) * 32 + (int)(e[j] & 31u);
+                int ux = ubx, uy = uby;
+                if (uo != 0xffffffffu) {
+                    const uint32_t wu = (uo >> 5) & 0x1fffffu;
+                    uy = (int)(wu / (uint32_t)pitch); ux = (int)(wu % (uint32_t)pitch) * 32 + (int)(uo & 31u);
+                }
+                nseg = close_segment(ox, oy, res, ux, uy, x, y, min_width, segs, nseg);
+                free_cells = 0;
+            }
+            uo = (active & ((v == 0u) | closing)) ? e[j] : uo;  // rp.py:514 / 516-518
+        }
+    }
+    return nseg;
+}
+
 struct RaycastArgs {
     const uint32_t* grids;
     size_t grid_stride_words;  // 0: every scenario uses the same grid
     GridView g;
     PathView pv;
     const int2* rowspan;
+    const uint32_t* ray_cells;  // [max_len][n_wp]
+    const int* ray_len;         // [n_wp], -1 = ray leaves the grid
     const int* wp_id;
     int first_offset, N;
     double min_width, sm;
@@ -407,17 +496,22 @@ raycast_kernel(RaycastArgs a) {
             phase ^= 1;
         }
         // ---- phase 1: free segments per horizon waypoint (rp.py:466-520), one lane per waypoint ----
-        for (int n = lane; n < N; n += 32) {
-            const int k = (first_w + n) % pv.n_wp;
-            int bad = 0, nseg;
-            if (MODE == 0)
-                nseg = walk_free_segments(g, pv.border + 4 * k, a.min_width, segs + n * kMaxSeg, bad,
-                                          [&](int y, int w) { return __ldg(gsrc + (size_t)y * g.pitch_words + w); });
-            else
-                nseg = walk_free_segments(g, pv.border + 4 * k, a.min_width, segs + n * kMaxSeg, bad,
-                                          [&](int y, int w) { return srow[(y - row0) * g.pitch_words + w]; });
-            if (bad || nseg > kMaxSeg) status |= MPC_ST_INDEX_ERROR;
-            nsegs[n] = nseg;
+        // MODE 0 reads the grid in global memory, MODES 1/2 the staged rows (row0 = first staged row)
+        const uint32_t* base = MODE == 0 ? gsrc : srow - (size_t)row0 * g.pitch_words;
+        for (int n0 = 0; n0 < N; n0 += 32) {
+            const int n = n0 + lane;
+            const int k = (first_w + (n < N ? n : 0)) % pv.n_wp;
+            int len = n < N ? a.ray_len[k] : 0;
+            if (len < 0) { status |= MPC_ST_INDEX_ERROR; len = 0; }
+            const int max_len_warp = __reduce_max_sync(0xffffffffu, len);
+            int ubx, uby;
+            w2m(g, pv.border[4 * k], pv.border[4 * k + 1], ubx, uby);  // the ray's start cell (rp.py:478, 488)
+            const int nseg = replay_ray(base, a.ray_cells, pv.n_wp, k, len, max_len_warp, ubx, uby, g.pitch_words, g.ox,
+                                        g.oy, g.res, a.min_width, segs + (n < N ? n : 0) * kMaxSeg, (uint32_t)(row0 * g.pitch_words));
+            if (n < N) {
+                if (nseg > kMaxSeg) status |= MPC_ST_INDEX_ERROR;
+                nsegs[n] = nseg;
+            }
         }
         __syncwarp();
         if (nsegs[0] == 0) status |= MPC_ST_NO_SEGMENT;  // rp.py:547 max([]) -> ValueError
@@ -541,12 +635,13 @@ int raycast_plan(const GridView& g, int N, bool shared_grid, int max_rows, bool 
 }
 
 void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridView& g, const PathView& pv,
-                    const int2* rowspan, int max_rows, const int* wp_id, int first_offset, int N, double min_width,
+                    const int2* rowspan, int max_rows, const uint32_t* ray_cells, const int* ray_len, const int* wp_id, int first_offset, int N, double min_width,
                     double sm, double* ub, double* lb, double* cells_sm, int* flags, int B, bool rowspan_ok,
                     cudaStream_t st, const double* state, int* wp_id_out, double* spatial_out, double length) {
     RaycastArgs a;
     a.state = state; a.wp_id_out = wp_id_out; a.spatial_out = spatial_out; a.length = length;
     a.grids = grids; a.grid_stride_words = grid_stride_words; a.g = g; a.pv = pv; a.rowspan = rowspan; a.wp_id = wp_id;
+    a.ray_cells = ray_cells; a.ray_len = ray_len;
     a.first_offset = first_offset; a.N = N; a.min_width = min_width; a.sm = sm; a.ub_out = ub; a.lb_out = lb;
     a.cells_sm_out = cells_sm; a.flags = flags; a.B = B;
     int warps = 8, stage_rows = 0;
