@@ -191,10 +191,11 @@ __global__ void localize_t2s_kernel(const double* __restrict__ state, int* __res
 // K3: ReferencePath.update_path_constraints (rp.py:522-648) on per-scenario bit-packed grids.
 // One warp per scenario.  The rows of the grid that the horizon's rays can touch are one
 // contiguous byte range (full 64 B-pitch rows): a single cp.async.bulk (TMA bulk copy, UBLKCP)
-// stages it in shared memory, signalled through an mbarrier.  Phase 1: lane n walks the ray of
-// horizon waypoint n (rp.py:466-520) and records its free segments; phase 2: every waypoint with
-// <= 1 candidate (or n == 0) is finalised independently; phase 3: the few waypoints with >= 2
-// candidates are resolved in order (nearest to the projected previous pick, rp.py:552-586).
+// stages it in shared memory, signalled through an mbarrier.  Phase 1: lane n replays the
+// precomputed cell sequence of horizon waypoint n's ray (ray table) against the scenario's grid and
+// records its free segments (rp.py:466-520); phase 2: every waypoint with <= 1 candidate (or n == 0)
+// is finalised independently; phase 3: the few waypoints with >= 2 candidates are resolved in
+// order (nearest to the projected previous pick, rp.py:552-586).
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxSeg = 8;
 
@@ -250,8 +251,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
     }
 }
 
-// closing a free segment (rp.py:503-515) is rare: keep its fp64 arithmetic out of line so that the three visit
-// sites of the walk stay small
+// closing a free segment (rp.py:503-515) is rare: keep its fp64 arithmetic out of line so that the replay loop
+// stays small
 __device__ __noinline__ int close_segment(double ox, double oy, double res, int uo_x, int uo_y, int x, int y,
                                           double min_width, short4* segs, int nseg) {
     const double ux = ((double)uo_x + 0.5) * res + ox, uy = ((double)uo_y + 0.5) * res + oy;  // map.py:98-99
@@ -261,74 +262,6 @@ __device__ __noinline__ int close_segment(double ox, double oy, double res, int 
         ++nseg;
     }
     return nseg;
-}
-
-// Walk the anti-aliased ray of one horizon waypoint over a bit grid and record its free segments
-// (rp.py:466-520).  `base[y * pitch + (x >> 5)]` is the grid word of cell (x, y).
-// The line walk emits up to three cells per step of the main chain (the chain cell and two anti-aliasing side
-// cells, in skimage's order); the three visits are PREDICATED rather than branched so that the 30 lanes of a
-// warp, which walk rays of different slopes, stay converged.  Only closing a free segment (rare) branches.
-// INSIDE = every emitted cell is known to be inside the grid (the usual case): no per-cell bounds checks.
-template <bool INSIDE>
-__device__ __forceinline__ int walk_ray(const uint32_t* __restrict__ base, int pitch, int W, int H, double ox, double oy,
-                                        double res, int ubx, int uby, int lbx, int lby, double min_width, short4* segs,
-                                        int& bad) {
-    int uo_x = ubx, uo_y = uby, free_cells = 0, nseg = 0;
-    auto visit = [&](int x, int y, bool active) {
-        int xx = x, yy = y;
-        if (!INSIDE) {  // numpy index semantics: negative wraps once, anything else is an IndexError
-            xx = x < 0 ? x + W : x; yy = y < 0 ? y + H : y;
-            if (xx < 0 || yy < 0 || xx >= W || yy >= H) { bad |= active; xx = 0; yy = 0; active = false; }
-        }
-        const uint32_t v = (base[yy * pitch + (xx >> 5)] >> (xx & 31)) & 1u;
-        free_cells |= (int)v & (int)active;
-        const bool at_end = (x == lbx) & (y == lby);
-        const bool closing = active & ((v == 0) | at_end) & (free_cells != 0);
-        if (closing) {
-            nseg = close_segment(ox, oy, res, uo_x, uo_y, x, y, min_width, segs, nseg);
-            free_cells = 0;
-        }
-        const bool move_uo = active & ((v == 0) | closing);  // rp.py:514 / 516-518
-        uo_x = move_uo ? x : uo_x;
-        uo_y = move_uo ? y : uo_y;
-    };
-    // skimage.draw.line_aa(x0, y0, x1, y1): r = x, c = y; the first emitted cell is skipped (rp.py:494, Q4)
-    const int r0 = ubx, c0 = uby, r1 = lbx, c1 = lby;
-    const int dc = abs(c0 - c1), dr = abs(r0 - r1);
-    float err = (float)(dc - dr);
-    const int sign_c = (c0 < c1) ? 1 : -1, sign_r = (r0 < r1) ? 1 : -1;
-    const float ed = (dc + dr == 0) ? 1.0f : (float)sqrt((double)(dc * dc + dr * dr));
-    const float fdc = (float)dc, fdr = (float)dr;
-    int c = c0, r = r0;
-    bool first = true;
-    for (;;) {
-        visit(r, c, !first);
-        first = false;
-        const float e0 = err;
-        const int c_prev = c;
-        const bool step_c = 2 * e0 >= -fdc;
-        if (step_c & (c == c1)) break;
-        visit(r + sign_r, c, step_c & (e0 + fdr < ed));
-        err -= step_c ? fdr : 0.0f;
-        c += step_c ? sign_c : 0;
-        const bool step_r = 2 * e0 <= fdr;
-        if (step_r & (r == r1)) break;
-        visit(r, c_prev + sign_c, step_r & (fdc - e0 < ed));
-        err += step_r ? fdc : 0.0f;
-        r += step_r ? sign_r : 0;
-    }
-    return nseg;
-}
-
-__device__ __forceinline__ int walk_free_segments(const GridView& g, const double* bc, double min_width, short4* segs,
-                                                  int& bad, const uint32_t* __restrict__ base) {
-    int ubx, uby, lbx, lby;
-    w2m(g, bc[0], bc[1], ubx, uby);  // rp.py:478
-    w2m(g, bc[2], bc[3], lbx, lby);  // rp.py:480
-    // every emitted cell lies within one pixel of the segment's bounding box
-    const bool inside = min(ubx, lbx) >= 1 && min(uby, lby) >= 1 && max(ubx, lbx) < g.W - 1 && max(uby, lby) < g.H - 1;
-    if (inside) return walk_ray<true>(base, g.pitch_words, g.W, g.H, g.ox, g.oy, g.res, ubx, uby, lbx, lby, min_width, segs, bad);
-    return walk_ray<false>(base, g.pitch_words, g.W, g.H, g.ox, g.oy, g.res, ubx, uby, lbx, lby, min_width, segs, bad);
 }
 
 // ------------------------------------------------------------------------------------------------
