@@ -1,6 +1,7 @@
 // admm.cu -- kernel entry points for K1+K2 (see admm.cuh).  FMA contraction is enabled here: the QP
 // solution is compared within a tolerance, not bit-for-bit.
 #include "engine.h"
+#include "admm_epilogue.cuh"
 #include <cstdio>
 #include <cstdlib>
 
@@ -30,31 +31,6 @@ __device__ __forceinline__ void write_solution(int N, int lane, const T w[5], do
     for (int i = 0; i < 3; ++i) xo[3 * lane + i] = (double)w[i];
     if (lane < N) { xo[3 * (N + 1) + 2 * lane] = (double)w[3]; xo[3 * (N + 1) + 2 * lane + 1] = (double)w[4]; }
 }
-
-// BicycleModel.drive (sbm.py:221-244) fused behind the solve on the closed-loop path.  Explicit round-to-nearest
-// intrinsics: this file is compiled with FMA contraction on, the standalone rollout_kernel without, and both
-// must produce the same bits.
-__device__ __forceinline__ void drive_one(double* __restrict__ state, int b, int B, double e_y, double e_psi,
-                                          double kappa_wp, double v, double delta, double L, double Ts) {
-    const double psi = state[2 * (size_t)B + b];
-    const double x_dot = __dmul_rn(v, cos(psi));                       // sbm.py:231
-    const double y_dot = __dmul_rn(v, sin(psi));                       // sbm.py:232
-    const double psi_dot = __dmul_rn(__ddiv_rn(v, L), tan(delta));     // sbm.py:233
-    state[b] = __dadd_rn(state[b], __dmul_rn(x_dot, Ts));              // sbm.py:237
-    state[(size_t)B + b] = __dadd_rn(state[(size_t)B + b], __dmul_rn(y_dot, Ts));
-    state[2 * (size_t)B + b] = __dadd_rn(psi, __dmul_rn(psi_dot, Ts));
-    const double s_dot = __dmul_rn(__dmul_rn(__ddiv_rn(1.0, __dsub_rn(1.0, __dmul_rn(e_y, kappa_wp))), v), cos(e_psi));  // sbm.py:240
-    state[3 * (size_t)B + b] = __dadd_rn(state[3 * (size_t)B + b], __dmul_rn(s_dot, Ts));  // sbm.py:244
-}
-
-struct RolloutArgs {  // non-null state: fuse the rollout of this scenario behind its solve
-    double* state;
-    const double* spatial;
-    const double* kappa;
-    int wp;
-    double Ts;
-    int B;
-};
 
 template <typename T, typename Comm>
 __device__ __forceinline__ void control_epilogue(Comm& cm, const MpcParams& mp, int lane, const T w[5], const SolveResult& r,
@@ -247,6 +223,16 @@ static void assemble_solve_block_launch(const MpcParams& mp, const AdmmSettings&
                                                                 x_out, iters, qp_status, flags, B, rs, Ts);
 }
 
+// MPC_ADMM_KERNEL=stage selects the lane-per-stage fp32 kernels (admm.cuh) instead of the paired-stage ones
+// (admm_pair.cuh) -- an A/B switch for tuning and for the parity tests, both are sm_100a CUDA.
+static bool use_pair_kernels() {
+    static const bool v = [] {
+        const char* e = getenv("MPC_ADMM_KERNEL");
+        return !(e && e[0] == 's');
+    }();
+    return v;
+}
+
 int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax,
                     const double* l, const double* u, double* x_out, int* iters, int* status, int B, cudaStream_t s) {
 #define WARP_GO(T_, L_) solve_qp_launch<T_, L_, Tune<T_>::rlev, Tune<T_>::minb>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s)
@@ -256,6 +242,8 @@ int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* 
     if (precision == 1) {
         if (ns <= 16) WARP_GO(double, 4); else if (ns <= 32) WARP_GO(double, 5);
         else if (ns <= 64) BLOCK_GO(double, 6, 64); else BLOCK_GO(double, 7, 128);
+    } else if (use_pair_kernels() && ns <= 64) {
+        return launch_solve_qp_pair(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s);
     } else {
         if (ns <= 16) WARP_GO(float, 4); else if (ns <= 32) WARP_GO(float, 5);
         else if (ns <= 64) BLOCK_GO(float, 6, 64); else BLOCK_GO(float, 7, 128);
@@ -276,6 +264,9 @@ int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings
     if (precision == 1) {
         if (ns <= 16) WARP_GO(double, 4); else if (ns <= 32) WARP_GO(double, 5);
         else if (ns <= 64) BLOCK_GO(double, 6, 64); else BLOCK_GO(double, 7, 128);
+    } else if (use_pair_kernels() && ns <= 64) {
+        return launch_assemble_solve_pair(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status,
+                                          flags, B, s, rollout_state, Ts);
     } else {
         if (ns <= 16) WARP_GO(float, 4); else if (ns <= 32) WARP_GO(float, 5);
         else if (ns <= 64) BLOCK_GO(float, 6, 64); else BLOCK_GO(float, 7, 128);

@@ -446,3 +446,195 @@ def admm_delta(N, Pd, q, Ax, l, u, dtype=np.float32, rho=0.1, sigma=1e-6, alpha=
     xs = (D * x).astype(np.float64)
     return dict(x=np.concatenate([xs[:, :3].ravel(), xs[:N, 3:].ravel()]), iter=it, status=status, drift=float(drift))
 
+
+
+# ------------------------------------------------------------------------------------------------------
+# "v-form" -- what csrc/admm_pair.cuh implements (fewer operations per iteration than the increment form)
+# ------------------------------------------------------------------------------------------------------
+# OSQP's row update is  v+ = alpha z~ + (1 - alpha) z + y / rho,  z+ = clip(v+),  y+ = rho (v+ - z+).  Because the previous
+# (z, y) came out of the same projection, y / rho = v - z and therefore  v+ = v + alpha (z~ - z) = v + w  with
+# w = alpha (r + A D), r = A x - z tracked.  A bound row is the triple (v, z, r); y is never stored (dy = rho (w - (z+ - z))
+# feeds the tracked u = q + A'y).  The dynamics rows are equalities whose z jumps from the cold start 0 to d in
+# iteration 1 and stays there: they carry r only, and iteration 1 is patched up afterwards (r -= d, u -= A'(rho d)).
+# When rho changes, v = z + (v - z) rho / rho+ (y itself is unchanged, as in OSQP).
+# (Tracking T = A'(y + rho r) through its increments instead, to save the second A' product per iteration, was tried
+#  and rejected: its rounding error accumulates and triples the fp32 error of the solution.)
+def admm_vform(N, Pd, q, Ax, l, u, dtype=np.float32, rho=0.1, sigma=1e-6, alpha=1.6, eps_abs=1e-3, eps_rel=1e-3,
+               eps_prim_inf=1e-4, eps_dual_inf=1e-4, max_iter=4000, scaling=10, check_termination=25,
+               adaptive_rho_interval=25, adaptive_rho_tolerance=5.0, paired=False):
+    dt = np.dtype(dtype); T = dt.type
+    s = from_reference_layout(N, Pd, q, Ax, l, u, dt)
+    L = N + 1
+    if paired:  # pad to an even number of stages >= the lane-group size the kernel uses
+        L2 = 16 if L <= 16 else (32 if L <= 32 else 64)
+        for k in ("a", "c", "e", "P", "q", "d", "lo", "hi"):
+            s[k] = np.concatenate([s[k], np.zeros((L2 - L, s[k].shape[1]), dt)])
+        L = L2
+    mask = np.ones((L, 5), bool); mask[N, 3:] = False; mask[N + 1:] = False
+    s["mask"] = mask
+    s["e"][N, 3:] = 0; s["lo"][N, 3:] = 0; s["hi"][N, 3:] = 0
+    ruiz(s, scaling, 5 * N + 3)
+    D, Ed, Eb, cs = s["D"], s["Ed"], s["Eb"], s["cs"]
+    lo, hi, dd, qq, P = s["lo"], s["hi"], s["d"], s["q"], s["P"]
+    thr = T(OSQP_INFTY * MIN_SCALING)
+    ctype = np.where((lo < -thr) & (hi > thr), -1, np.where(hi - lo < T(RHO_TOL), 1, 0))
+
+    def rho_vec(r):
+        return np.where(ctype == -1, T(RHO_MIN), np.where(ctype == 1, T(RHO_EQ_OVER_RHO_INEQ * r), T(r))).astype(dt)
+    fac = factorize_cr if paired else factorize
+    sol = solve_cr if paired else solve
+    rho = T(rho); rb = rho_vec(rho)
+    s["P"][N, 3:] = 1.0; fac(s, sigma, rho, rb); s["P"][N, 3:] = 0.0
+    rd = T(RHO_EQ_OVER_RHO_INEQ * rho)
+    al = T(alpha); status = 0
+    x = np.zeros((L, 5), dt)
+    vb = np.zeros((L, 5), dt); zb = np.zeros((L, 5), dt); rbd = np.zeros((L, 5), dt); rdy = np.zeros((L, 3), dt)
+    uu = qq.copy()  # u = q + A'y
+    for it in range(1, max_iter + 1):
+        g = np.where(mask, -((P * x + uu) + At_apply(s, rd * rdy, rb * rbd)), 0).astype(dt)
+        dl = (al * sol(s, g)).astype(dt)
+        s1d, s1b = A_apply(s, dl)
+        x = (x + dl).astype(dt); dx = dl
+        wd = (al * rdy + s1d).astype(dt)
+        rdy = (rdy + s1d).astype(dt)
+        dyd = (rd * wd).astype(dt)
+        wb = (al * rbd + s1b).astype(dt)
+        vb = (vb + wb).astype(dt)
+        zn = np.minimum(np.maximum(vb, lo), hi).astype(dt)
+        stepb = (zn - zb).astype(dt); zb = zn
+        rbd = ((rbd + s1b) - stepb).astype(dt)
+        dyb = (rb * (wb - stepb)).astype(dt)
+        uu = (uu + At_apply(s, dyd, dyb)).astype(dt)
+        if it == 1:  # the dynamics z jumped 0 -> d
+            rdy = (rdy - dd).astype(dt)
+            dyd = (dyd - rd * dd).astype(dt)
+            uu = (uu + At_apply(s, -rd * dd, np.zeros_like(dyb))).astype(dt)
+        if it % check_termination == 0 or it % adaptive_rho_interval == 0:
+            Axd, Axb = A_apply(s, x)
+            rpd, rpb = Axd - dd, Axb - zb
+            Px = P * x
+            Aty = uu - qq
+            rdual = np.where(mask, Px + uu, 0)
+            pri_res = max(np.max(np.abs(rpd / Ed)), np.max(np.abs(rpb / Eb)))
+            dua_res = np.max(np.abs(rdual / D)) / cs
+            if it % check_termination == 0:
+                nz_ = max(np.max(np.abs(dd / Ed)), np.max(np.abs(zb / Eb)))
+                nax = max(np.max(np.abs(Axd / Ed)), np.max(np.abs(Axb / Eb)))
+                eps_prim = eps_abs + eps_rel * max(nz_, nax)
+                nd = max(np.max(np.abs(qq / D)), np.max(np.abs(Aty / D)), np.max(np.abs(Px / D))) / cs
+                eps_dual = eps_abs + eps_rel * nd
+                if pri_res < eps_prim and dua_res < eps_dual: status = 1; break
+                if not (pri_res < eps_prim):
+                    pyd = dyd
+                    pyb = np.where(hi > thr, np.where(lo < -thr, 0, np.minimum(dyb, 0)), np.where(lo < -thr, np.maximum(dyb, 0), dyb))
+                    ndy = max(np.max(np.abs(Ed * pyd)), np.max(np.abs(Eb * pyb)))
+                    if ndy > eps_prim_inf:
+                        lhs = np.sum(dd * pyd) + np.sum(hi * np.maximum(pyb, 0) + lo * np.minimum(pyb, 0))
+                        if lhs < -eps_prim_inf * ndy:
+                            Atdy = np.where(mask, At_apply(s, pyd, pyb), 0)
+                            if np.max(np.abs(Atdy / D)) < eps_prim_inf * ndy: status = -3; break
+            if it % adaptive_rho_interval == 0:
+                pn = max(np.abs(rpd).max(), np.abs(rpb).max())
+                pn /= max(np.max(np.abs(dd)), np.max(np.abs(zb)), np.max(np.abs(Axd)), np.max(np.abs(Axb))) + 1e-10
+                dn = np.max(np.abs(rdual)); dn /= max(np.max(np.abs(qq)), np.max(np.abs(Aty)), np.max(np.abs(Px))) + 1e-10
+                rnew = float(rho) * np.sqrt(pn / (dn + 1e-10)); rnew = min(max(rnew, RHO_MIN), RHO_MAX)
+                if rnew > float(rho) * adaptive_rho_tolerance or rnew < float(rho) / adaptive_rho_tolerance:
+                    rb_old = rb
+                    rho = T(rnew); rb = rho_vec(rho); rd = T(RHO_EQ_OVER_RHO_INEQ * rho)
+                    vb = (zb + (vb - zb) * (rb_old / rb)).astype(dt)
+                    s["P"][N, 3:] = 1.0; fac(s, sigma, rho, rb); s["P"][N, 3:] = 0.0
+    if status == 0: status = -2
+    xs = (D * x).astype(np.float64)
+    return dict(x=np.concatenate([xs[:N + 1, :3].ravel(), xs[:N, 3:].ravel()]), iter=it, status=status)
+
+
+# ------------------------------------------------------------------------------------------------------
+# paired-stage factorisation: one level of cyclic reduction inside the lane, then PCR across lanes
+# ------------------------------------------------------------------------------------------------------
+# Lane l holds stages A = 2l and B = 2l + 1.  After the inputs are eliminated (as in factorize()), the even stages are
+# eliminated locally:  x_A = DA^-1 b_A - G x_B - H x_B(l-1)  with  G = DA^-1 U_A,  H = DA^-1 Lo_A;  the odd stages then
+# form a block-tridiagonal chain of half the length,
+#     D_B' = D_B - U_A' G - U_B H(l+1),   U_B' = -U_B G(l+1),   b_B' = b_B - G' b_A - [H' b_A](l+1),
+# which PCR solves in log2(lanes) levels.  csrc/admm_pair.cuh is the CUDA transcription.
+def _stage_blocks(s, sigma, rho, rho_b):
+    dt = s["a"].dtype
+    a, c, e, P = s["a"], s["c"], s["e"], s["P"]
+    L = a.shape[0]
+    rd = dt.type(RHO_EQ_OVER_RHO_INEQ * rho)
+    diag = P + dt.type(sigma) + rho_b * e * e
+    cn = down(c)
+    Sxx = np.zeros((L, 3, 3), dt)
+    Sxx[:, 0, 0] = diag[:, 0] + rd * (c[:, 0] ** 2 + a[:, 0] ** 2 + a[:, 2] ** 2 + a[:, 4] ** 2)
+    Sxx[:, 1, 1] = diag[:, 1] + rd * (c[:, 1] ** 2 + a[:, 1] ** 2 + a[:, 3] ** 2)
+    Sxx[:, 2, 2] = diag[:, 2] + rd * (c[:, 2] ** 2 + a[:, 5] ** 2)
+    Sxx[:, 0, 1] = Sxx[:, 1, 0] = rd * (a[:, 0] * a[:, 1] + a[:, 2] * a[:, 3])
+    Sxx[:, 0, 2] = Sxx[:, 2, 0] = rd * (a[:, 4] * a[:, 5])
+    Svv = diag[:, 3] + rd * a[:, 7] ** 2
+    Skk = diag[:, 4] + rd * a[:, 6] ** 2
+    Sxv = np.stack([rd * a[:, 4] * a[:, 7], np.zeros(L, dt), rd * a[:, 5] * a[:, 7]], axis=1)
+    Sxk = np.stack([rd * a[:, 2] * a[:, 6], rd * a[:, 3] * a[:, 6], np.zeros(L, dt)], axis=1)
+    Fx = np.zeros((L, 3, 3), dt)
+    Fx[:, 0, 0] = rd * a[:, 0] * cn[:, 0]; Fx[:, 1, 0] = rd * a[:, 1] * cn[:, 0]
+    Fx[:, 0, 1] = rd * a[:, 2] * cn[:, 1]; Fx[:, 1, 1] = rd * a[:, 3] * cn[:, 1]
+    Fx[:, 0, 2] = rd * a[:, 4] * cn[:, 2]; Fx[:, 2, 2] = rd * a[:, 5] * cn[:, 2]
+    Fv = rd * a[:, 7] * cn[:, 2]
+    Fk = rd * a[:, 6] * cn[:, 1]
+    iv, ik = (1.0 / Svv).astype(dt), (1.0 / Skk).astype(dt)
+    Dm = Sxx - iv[:, None, None] * Sxv[:, :, None] * Sxv[:, None, :] - ik[:, None, None] * Sxk[:, :, None] * Sxk[:, None, :]
+    U = Fx.copy()
+    U[:, :, 2] -= (iv * Fv)[:, None] * Sxv
+    U[:, :, 1] -= (ik * Fk)[:, None] * Sxk
+    addn = up(np.stack([np.zeros(L, dt), ik * Fk * Fk, iv * Fv * Fv], axis=1))
+    for i in range(3):
+        Dm[:, i, i] -= addn[:, i]
+    U[-1] = 0
+    return Dm.astype(dt), U.astype(dt), dict(iv=iv, ik=ik, Sxv=Sxv, Sxk=Sxk, Fv=Fv, Fk=Fk)
+
+
+def factorize_cr(s, sigma, rho, rho_b):
+    dt = s["a"].dtype
+    Dm, U, f = _stage_blocks(s, sigma, rho, rho_b)
+    L = Dm.shape[0]
+    assert L % 2 == 0
+    DA, DB, UA, UB = Dm[0::2], Dm[1::2], U[0::2], U[1::2]
+    LoA = np.transpose(up(UB), (0, 2, 1))          # couples A_l to B_(l-1)
+    DAi = inv3(DA)
+    G = np.einsum("lij,ljk->lik", DAi, UA).astype(dt)
+    H = np.einsum("lij,ljk->lik", DAi, LoA).astype(dt)
+    Dr = (DB - np.einsum("lji,ljk->lik", UA, G) - np.einsum("lij,ljk->lik", UB, down(H))).astype(dt)
+    Ur = (-np.einsum("lij,ljk->lik", UB, down(G))).astype(dt)
+    Ur[-1] = 0
+    Lr = np.transpose(up(Ur), (0, 2, 1)).copy()
+    levels = []
+    sft = 1
+    n = L // 2
+    while sft < n:
+        Dinv = inv3(Dr)
+        al = np.einsum("lij,ljk->lik", Lr, up(Dinv, sft))
+        be = np.einsum("lij,ljk->lik", Ur, down(Dinv, sft))
+        Dr = (Dr - np.einsum("lij,ljk->lik", al, up(Ur, sft)) - np.einsum("lij,ljk->lik", be, down(Lr, sft))).astype(dt)
+        Lr, Ur = (-np.einsum("lij,ljk->lik", al, up(Lr, sft))).astype(dt), (-np.einsum("lij,ljk->lik", be, down(Ur, sft))).astype(dt)
+        levels.append((al.astype(dt), be.astype(dt), sft))
+        sft *= 2
+    f.update(levels=levels, Dinv=inv3(Dr), DAi=DAi, G=G, H=H)
+    s["fac"] = f
+
+
+def solve_cr(s, b):
+    f = s["fac"]
+    bx = b[:, :3] - (f["iv"] * b[:, 3])[:, None] * f["Sxv"] - (f["ik"] * b[:, 4])[:, None] * f["Sxk"]
+    tn = np.stack([np.zeros_like(b[:, 0]), f["ik"] * f["Fk"] * b[:, 4], f["iv"] * f["Fv"] * b[:, 3]], axis=1)
+    bx = bx - up(tn)
+    bA, bB = bx[0::2], bx[1::2]
+    tH = np.einsum("lji,lj->li", f["H"], bA)
+    br = bB - np.einsum("lji,lj->li", f["G"], bA) - down(tH)
+    for al, be, sft in f["levels"]:
+        br = br - np.einsum("lij,lj->li", al, up(br, sft)) - np.einsum("lij,lj->li", be, down(br, sft))
+    xB = np.einsum("lij,lj->li", f["Dinv"], br)
+    xA = np.einsum("lij,lj->li", f["DAi"], bA) - np.einsum("lij,lj->li", f["G"], xB) - np.einsum("lij,lj->li", f["H"], up(xB))
+    x = np.empty_like(bx)
+    x[0::2], x[1::2] = xA, xB
+    xn = down(x)
+    v = f["iv"] * (b[:, 3] - np.einsum("li,li->l", f["Sxv"], x) - f["Fv"] * xn[:, 2])
+    k = f["ik"] * (b[:, 4] - np.einsum("li,li->l", f["Sxk"], x) - f["Fk"] * xn[:, 1])
+    return np.concatenate([x, v[:, None], k[:, None]], axis=1).astype(b.dtype)
