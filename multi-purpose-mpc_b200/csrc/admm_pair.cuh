@@ -189,8 +189,9 @@ __device__ __forceinline__ void ruiz_scale2(const GroupComm<LPS>& cm, Stage2& s,
 template <int LPS> struct PairFactor {
     static constexpr int NLEV = LPS == 32 ? 5 : (LPS == 16 ? 4 : (LPS == 8 ? 3 : 2));
     f2 iv, ik, nsxv0, nsxv2, nsxk0, nsxk1, nfv, nfk;  // input elimination (per stage); couplings stored negated
-    float G[9], H[9], DAi[6];                   // in-lane cyclic-reduction level
-    f2 ab[NLEV - 1][9];                         // PCR levels 0 .. NLEV-2: (alpha, beta) packed
+    float UA[6], LA[6], DAi[6];                 // in-lane cyclic-reduction level: nonzeros of U_A (0 1 2 3 4 8), of Lo_A
+                                                // (= U_B(l-1)': same six, transposed), DA^-1 (symmetric)
+    f2 nab[NLEV - 1][9];                        // PCR levels 0 .. NLEV-2: (-alpha, -beta) packed
     float last[9];                              // PCR level NLEV-1: one partner (gl ^ LPS/2)
     float Dinv[6];                              // symmetric: 00 01 02 11 12 22
 };
@@ -275,11 +276,14 @@ __device__ __forceinline__ void factorize2(const GroupComm<LPS>& cm, const Stage
         LoA[3] = p1; LoA[4] = p4; LoA[5] = 0.0f;
         LoA[6] = p2; LoA[7] = 0.0f; LoA[8] = p8;
     }
-    mm3(Di9, UA, f.G);
-    mm3(Di9, LoA, f.H);
+    float G[9], H[9];  // G = DA^-1 U_A, H = DA^-1 Lo_A
+    mm3(Di9, UA, G);
+    mm3(Di9, LoA, H);
+    f.UA[0] = UA[0]; f.UA[1] = UA[1]; f.UA[2] = UA[2]; f.UA[3] = UA[3]; f.UA[4] = UA[4]; f.UA[5] = UA[8];
+    f.LA[0] = LoA[0]; f.LA[1] = LoA[3]; f.LA[2] = LoA[6]; f.LA[3] = LoA[1]; f.LA[4] = LoA[4]; f.LA[5] = LoA[8];
     float Hn[9], Gn[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { Hn[i] = cm.next(f.H[i]); Gn[i] = cm.next(f.G[i]); }
+    for (int i = 0; i < 9; ++i) { Hn[i] = cm.next(H[i]); Gn[i] = cm.next(G[i]); }
     float Dm[9], U[9], Lo[9];
     {
         const float DB[9] = {D00.y, D01.y, D02.y, D01.y, D11.y, 0.0f, D02.y, 0.0f, D22.y};
@@ -289,7 +293,7 @@ __device__ __forceinline__ void factorize2(const GroupComm<LPS>& cm, const Stage
             for (int k = 0; k < 3; ++k) {
                 float acc = DB[3 * i + k];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) acc -= UA[3 * j + i] * f.G[3 * j + k] + UB[3 * i + j] * Hn[3 * j + k];
+                for (int j = 0; j < 3; ++j) acc -= UA[3 * j + i] * G[3 * j + k] + UB[3 * i + j] * Hn[3 * j + k];
                 Dm[3 * i + k] = acc;
             }
         float t[9];
@@ -333,7 +337,7 @@ __device__ __forceinline__ void factorize2(const GroupComm<LPS>& cm, const Stage
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
             Lo[i] = -t1[i]; U[i] = -t2[i];
-            if (lev < NLEV - 1) f.ab[lev < NLEV - 1 ? lev : 0][i] = mk(al[i], be[i]);
+            if (lev < NLEV - 1) f.nab[lev < NLEV - 1 ? lev : 0][i] = mk(-al[i], -be[i]);
             else f.last[i] = has_up ? al[i] : be[i];
         }
     }
@@ -352,29 +356,33 @@ __device__ __forceinline__ void kkt_solve2(const GroupComm<LPS>& cm, const PairF
     f2 bx2 = pfma(bv, f.nsxv2, b[2]);
     bx1 = padd(bx1, cm.to_next(pmul(bk, f.nfk)));
     bx2 = padd(bx2, cm.to_next(pmul(bv, f.nfv)));
-    // in-lane cyclic-reduction level: b_B' = b_B - G' b_A - [H' b_A](l+1)
+    // in-lane cyclic-reduction level: t = DA^-1 b_A,  b_B' = b_B - U_A' t - [Lo_A' t](l+1)
     const float bA0 = bx0.x, bA1 = bx1.x, bA2 = bx2.x;
-    float r0 = bx0.y, r1 = bx1.y, r2 = bx2.y;
-    const float h0 = fmaf(f.H[6], bA2, fmaf(f.H[3], bA1, f.H[0] * bA0));
-    const float h1 = fmaf(f.H[7], bA2, fmaf(f.H[4], bA1, f.H[1] * bA0));
-    const float h2 = fmaf(f.H[8], bA2, fmaf(f.H[5], bA1, f.H[2] * bA0));
-    r0 = fmaf(-f.G[6], bA2, fmaf(-f.G[3], bA1, fmaf(-f.G[0], bA0, r0)));
-    r1 = fmaf(-f.G[7], bA2, fmaf(-f.G[4], bA1, fmaf(-f.G[1], bA0, r1)));
-    r2 = fmaf(-f.G[8], bA2, fmaf(-f.G[5], bA1, fmaf(-f.G[2], bA0, r2)));
-    r0 -= cm.next(h0); r1 -= cm.next(h1); r2 -= cm.next(h2);
-    // PCR: (p, q) accumulate the up- and the down-neighbour products in one packed FMA
+    const float t0 = fmaf(f.DAi[2], bA2, fmaf(f.DAi[1], bA1, f.DAi[0] * bA0));
+    const float t1 = fmaf(f.DAi[4], bA2, fmaf(f.DAi[3], bA1, f.DAi[1] * bA0));
+    const float t2 = fmaf(f.DAi[5], bA2, fmaf(f.DAi[4], bA1, f.DAi[2] * bA0));
+    // U_A = [u0 u1 u2; u3 u4 0; 0 0 u5],  Lo_A = [l0 l3 0; l1 l4 0; l2 0 l5]   (indices into f.UA / f.LA)
+    const float h0 = fmaf(f.LA[2], t2, fmaf(f.LA[1], t1, f.LA[0] * t0));
+    const float h1 = fmaf(f.LA[4], t1, f.LA[3] * t0);
+    const float h2 = f.LA[5] * t2;
+    f2 R0 = mk(fmaf(-f.UA[3], t1, fmaf(-f.UA[0], t0, bx0.y)), 0.0f);
+    f2 R1 = mk(fmaf(-f.UA[4], t1, fmaf(-f.UA[1], t0, bx1.y)), 0.0f);
+    f2 R2 = mk(fmaf(-f.UA[5], t2, fmaf(-f.UA[2], t0, bx2.y)), 0.0f);
+    R0.x -= cm.next(h0); R1.x -= cm.next(h1); R2.x -= cm.next(h2);
+    // PCR: one packed FMA chain per row accumulates r - alpha.up - beta.down as (r - alpha.up, -beta.down)
 #pragma unroll
     for (int lev = 0; lev < NLEV - 1; ++lev) {
         const int sft = 1 << lev;
-        const f2 n0 = mk(cm.up(r0, sft), cm.dn(r0, sft));
-        const f2 n1 = mk(cm.up(r1, sft), cm.dn(r1, sft));
-        const f2 n2 = mk(cm.up(r2, sft), cm.dn(r2, sft));
-        const f2* ab = f.ab[lev];
-        const f2 s0 = pfma(ab[2], n2, pfma(ab[1], n1, pmul(ab[0], n0)));
-        const f2 s1 = pfma(ab[5], n2, pfma(ab[4], n1, pmul(ab[3], n0)));
-        const f2 s2 = pfma(ab[8], n2, pfma(ab[7], n1, pmul(ab[6], n0)));
-        r0 -= s0.x + s0.y; r1 -= s1.x + s1.y; r2 -= s2.x + s2.y;
+        const f2 n0 = mk(cm.up(R0.x, sft), cm.dn(R0.x, sft));
+        const f2 n1 = mk(cm.up(R1.x, sft), cm.dn(R1.x, sft));
+        const f2 n2 = mk(cm.up(R2.x, sft), cm.dn(R2.x, sft));
+        const f2* nab = f.nab[lev];
+        const f2 s0 = pfma(nab[2], n2, pfma(nab[1], n1, pfma(nab[0], n0, R0)));
+        const f2 s1 = pfma(nab[5], n2, pfma(nab[4], n1, pfma(nab[3], n0, R1)));
+        const f2 s2 = pfma(nab[8], n2, pfma(nab[7], n1, pfma(nab[6], n0, R2)));
+        R0.x = s0.x + s0.y; R1.x = s1.x + s1.y; R2.x = s2.x + s2.y;
     }
+    float r0 = R0.x, r1 = R1.x, r2 = R2.x;
     {
         const int sft = LPS / 2;
         const float n0 = cm.bfly(r0, sft), n1 = cm.bfly(r1, sft), n2 = cm.bfly(r2, sft);
@@ -385,18 +393,15 @@ __device__ __forceinline__ void kkt_solve2(const GroupComm<LPS>& cm, const PairF
     const float xB0 = fmaf(f.Dinv[2], r2, fmaf(f.Dinv[1], r1, f.Dinv[0] * r0));
     const float xB1 = fmaf(f.Dinv[4], r2, fmaf(f.Dinv[3], r1, f.Dinv[1] * r0));
     const float xB2 = fmaf(f.Dinv[5], r2, fmaf(f.Dinv[4], r1, f.Dinv[2] * r0));
-    // back-substitution: x_A = DA^-1 b_A - G x_B - H x_B(l-1)
+    // back-substitution: x_A = t - DA^-1 (U_A x_B + Lo_A x_B(l-1))
     const float p0 = cm.prev(xB0), p1 = cm.prev(xB1), p2 = cm.prev(xB2);
-    float xA0 = fmaf(f.DAi[2], bA2, fmaf(f.DAi[1], bA1, f.DAi[0] * bA0));
-    float xA1 = fmaf(f.DAi[4], bA2, fmaf(f.DAi[3], bA1, f.DAi[1] * bA0));
-    float xA2 = fmaf(f.DAi[5], bA2, fmaf(f.DAi[4], bA1, f.DAi[2] * bA0));
-    float g0 = fmaf(f.G[2], xB2, fmaf(f.G[1], xB1, f.G[0] * xB0));
-    float g1 = fmaf(f.G[5], xB2, fmaf(f.G[4], xB1, f.G[3] * xB0));
-    float g2 = fmaf(f.G[8], xB2, fmaf(f.G[7], xB1, f.G[6] * xB0));
-    xA0 = fmaf(-f.H[2], p2, fmaf(-f.H[1], p1, fmaf(-f.H[0], p0, xA0)));
-    xA1 = fmaf(-f.H[5], p2, fmaf(-f.H[4], p1, fmaf(-f.H[3], p0, xA1)));
-    xA2 = fmaf(-f.H[8], p2, fmaf(-f.H[7], p1, fmaf(-f.H[6], p0, xA2)));
-    x[0] = mk(xA0 - g0, xB0); x[1] = mk(xA1 - g1, xB1); x[2] = mk(xA2 - g2, xB2);
+    const float w0 = fmaf(f.LA[3], p1, fmaf(f.LA[0], p0, fmaf(f.UA[2], xB2, fmaf(f.UA[1], xB1, f.UA[0] * xB0))));
+    const float w1 = fmaf(f.LA[4], p1, fmaf(f.LA[1], p0, fmaf(f.UA[4], xB1, f.UA[3] * xB0)));
+    const float w2 = fmaf(f.LA[5], p2, fmaf(f.LA[2], p0, f.UA[5] * xB2));
+    const float xA0 = fmaf(-f.DAi[2], w2, fmaf(-f.DAi[1], w1, fmaf(-f.DAi[0], w0, t0)));
+    const float xA1 = fmaf(-f.DAi[4], w2, fmaf(-f.DAi[3], w1, fmaf(-f.DAi[1], w0, t1)));
+    const float xA2 = fmaf(-f.DAi[5], w2, fmaf(-f.DAi[4], w1, fmaf(-f.DAi[2], w0, t2)));
+    x[0] = mk(xA0, xB0); x[1] = mk(xA1, xB1); x[2] = mk(xA2, xB2);
     const f2 xn1 = cm.from_next(x[1]), xn2 = cm.from_next(x[2]);  // fv, fk are 0 where there is no successor
     x[3] = pmul(f.iv, pfma(f.nfv, xn2, pfma(f.nsxv2, x[2], pfma(f.nsxv0, x[0], b[3]))));
     x[4] = pmul(f.ik, pfma(f.nfk, xn1, pfma(f.nsxk1, x[1], pfma(f.nsxk0, x[0], b[4]))));
@@ -517,8 +522,10 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
         emit(w, r);
         done = true;
     };
-    for (iter = 1; iter <= st.max_iter; ++iter) {
-        f2 td[3], tb[5], rhs[5], dl[5], s1d[3], s1b[5], ed[3], eb[5];
+    // one ADMM pass
+    f2 dl[5], ed[3], eb[5];
+    auto pass = [&](const bool first) __attribute__((always_inline)) {
+        f2 td[3], tb[5], rhs[5], s1d[3], s1b[5];
 #pragma unroll
         for (int i = 0; i < 3; ++i) td[i] = pmul(rd, rdy[i]);
 #pragma unroll
@@ -548,19 +555,18 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
             rbd[i] = psub(padd(rbd[i], s1b[i]), step);
             eb[i] = pmul(rb[i], psub(wv, step));      // dy of the bound rows
         }
-        At_apply2<LPS, LOOSE>(cm, s, ed, eb, u, u);
-        if (iter == 1) {  // the dynamics z jumped from the cold start 0 to d
-            f2 nd[3];
+        if (first) {  // iteration 1: the dynamics z jumped from the cold start 0 to d (z+ - z = d instead of 0)
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const f2 dd = ldsv(&sm[i * LPS + gl]);
                 rdy[i] = psub(rdy[i], dd);
-                nd[i] = pmul(pmul(rd, dd), kNegOne2);
-                ed[i] = padd(ed[i], nd[i]);
+                ed[i] = psub(ed[i], pmul(rd, dd));
             }
-            const f2 zb0[5] = {zero, zero, zero, zero, zero};
-            At_apply2<LPS, LOOSE>(cm, s, nd, zb0, u, u);
         }
+        At_apply2<LPS, LOOSE>(cm, s, ed, eb, u, u);
+    };
+    // termination check / rho adaptation after a pass; returns true when every scenario of the warp is done
+    auto after_pass = [&]() __attribute__((always_inline)) -> bool {
         const bool can_check = (--chk == 0), can_adapt = (--adp == 0);
         if (can_check) chk = st.check_termination;
         if (can_adapt) adp = st.adaptive_rho_interval;
@@ -692,7 +698,7 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
                 if (status == 0 && pinf) status = -3;
                 if (status == 0 && dinf) status = -4;
                 if (!done && status != 0) finish(status, iter);
-                if (GC::warp_all(done)) break;
+                if (GC::warp_all(done)) return true;
             }
             if (can_adapt) {  // adapt_rho / compute_rho_estimate on the scaled residuals
                 const float pn = pr_s / (fmaxf(nz_s, nax_s) + 1e-10f);
@@ -722,6 +728,11 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
                 }
             }
         }
+        return false;
+    };
+    for (iter = 1; iter <= st.max_iter; ++iter) {
+        pass(iter == 1);
+        if (after_pass()) break;
     }
     if (GC::warp_any(!done)) {
         // max_iter reached: OSQP re-checks the residuals with 10x looser tolerances and reports
