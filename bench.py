@@ -264,7 +264,18 @@ def main():
     except Exception:
         pass
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
-    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # nominal: no measured FP32-pipe figure exists in MEASURED_PEAKS.json
+    # FP32 CUDA-core peak: MEASURED_PEAKS.json has no such figure, so the denominator is the FFMA issue rate measured on
+    # this pool's B200 with tools/pipe_microbench.cu (profiles/measured_fp32_peak.json); nominal only if that is missing
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    fp32_src = "nominal 148 SM x 128 lanes x 2 x sm_max_mhz"
+    try:
+        mp_ = json.load(open(os.path.join(REPO, "profiles", "measured_fp32_peak.json")))
+        fp32_peak = float(mp_["fp32_tflops"])
+        fp32_src = ("measured: %.3f FFMA warp-instr/clk/SM x 32 x 2 x %d SMs x %.3f GHz (tools/pipe_microbench.cu, "
+                    "profiles/measured_fp32_peak.json); nominal is %.1f" % (mp_["ffma_warp_instr_per_clk_per_sm"], mp_["sms"],
+                                                                          mp_["clock_khz"] / 1e6, 148 * 128 * 2 * sm_max * 1e6 / 1e12))
+    except Exception:
+        pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     rollout_gbs = 100.0 * B / (kernel_ms["rollout"] * 1e-3) / 1e9 if kernel_ms["rollout"] > 0 else None
     # raycast: algorithmic bytes = 32 B x distinct 32-byte sectors of the bit grid holding a tested cell + 16N + 32
@@ -337,15 +348,16 @@ def main():
                     "d2h_bytes_per_step": int(6 * B * 8 + 4 * B)},
             "gpu_launches": int(launches),
             "kernel_ms": kernel_ms,
-            "roofline": {"kernel": "assemble_solve_kernel<float,5> (K1+K2)" if args.precision == 0 else "assemble_solve_kernel<double,5>",
+            "roofline": {"kernel": ("assemble_solve_pair_kernel<16,loose> (K1+K2+K4b, paired-stage fp32)" if os.environ.get("MPC_ADMM_KERNEL", "p")[0] != "s"
+                                    else "assemble_solve_kernel<float,5> (K1+K2)") if args.precision == 0 else "assemble_solve_kernel<double,5>",
                          "bound": "fp32_pipe" if args.precision == 0 else "fp64_pipe", "achieved": achieved,
                          "peak": fp32_peak if args.precision == 0 else fp32_peak / 2, "unit": "TFLOP/s",
                          "frac": achieved / (fp32_peak if args.precision == 0 else fp32_peak / 2),
-                         "peak_source": "nominal 148 SM x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json has no CUDA-core figure)",
+                         "peak_source": fp32_src + " (MEASURED_PEAKS.json has no CUDA-core figure)",
                          "flops_per_launch": flops_per_launch,
-                         "traffic": 3.87e6 * B / 4096 if args.precision == 0 else None,
+                         "traffic": 4.19e6 * B / 4096 if args.precision == 0 else None,
                          "traffic_source": "dram__bytes_read+write of one launch at 4096 scenarios, ncu --set full "
-                                           "(profiles/r1_assemble_solve_fp32.txt), scaled by batch",
+                                           "(profiles/r1_assemble_solve_pair_fp32.txt), scaled by batch",
                          "model": "SURVEY 8d: iters*(340N+264) + 400(N+1) + (iters/25)*(142N+78) per instance, actual iteration counts"},
             "roofline_hbm": [
                 {"kernel": "rollout_kernel (K4)", "bound": "hbm", "achieved": rollout_gbs, "peak": hbm_peak, "unit": "GB/s",

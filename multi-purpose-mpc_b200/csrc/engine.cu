@@ -245,7 +245,8 @@ static int compute_rowspan(mpc_engine* h) {
         const long dy = std::labs((long)std::floor((b[1] - h->g.oy) / h->g.res) - (long)std::floor((b[3] - h->g.oy) / h->g.res));
         max_len = std::max(max_len, (int)std::min<long>(3 * (dx + dy) + 4, 1 << 20));
     }
-    if ((size_t)h->words >= (1u << 21)) return fail(MPC_E_UNSUPPORTED, "grid too large for the packed ray table");
+    if ((size_t)h->words >= (1u << 26)) return fail(MPC_E_UNSUPPORTED, "grid too large for the packed ray table");
+    max_len = (max_len + 7) & ~7;  // the replay fetches 8 entries at a time and reads the padding of shorter rays
     h->ray_max_len = max_len;
     CUDA_OK(h->d_ray_cells.alloc((size_t)max_len * n));
     CUDA_OK(h->d_ray_len.alloc(n));

@@ -173,6 +173,32 @@ __device__ __forceinline__ int localize_one(const double* __restrict__ state, do
     return w;
 }
 
+// The same for a whole warp working on one car: the search over the cumulative lengths is spread over the lanes
+// (independent loads instead of a chain of dependent ones; length_cum is non-decreasing, so the first index with
+// length_cum > s is the number of entries <= s).  Returns the waypoint in every lane; lane 0 writes `spatial`.
+__device__ __forceinline__ int localize_warp(const double* __restrict__ state, double* __restrict__ spatial,
+                                             const PathView& pv, double length, int b, int B, int lane) {
+    const double s = state[3 * (size_t)B + b];
+    int cnt = 0;
+    for (int i = lane; i < pv.n_wp; i += 32) cnt += (pv.length_cum[i] > s) ? 0 : 1;
+    const int lo = __reduce_add_sync(0xffffffffu, cnt);
+    if (lo >= pv.n_wp || !(s < length)) return -1;
+    const int next = lo, prev = next > 0 ? next - 1 : pv.n_wp - 1;  // index -1 wraps in numpy
+    int w = 0;
+    if (lane == 0) {
+        const double x = state[b], y = state[(size_t)B + b], psi = state[2 * (size_t)B + b];
+        const double s_next = pv.length_cum[next], s_prev = pv.length_cum[prev];
+        w = (fabs(s - s_next) < fabs(s - s_prev)) ? next : prev;  // strict <: ties -> prev (quirk Q8)
+        const double e_y = pv.cos_psi[w] * (y - pv.y[w]) - pv.sin_psi[w] * (x - pv.x[w]);  // sbm.py:202-205
+        const double PI = 3.141592653589793;
+        double e_psi = psi - pv.psi[w];
+        e_psi = np_mod(e_psi + PI, 2 * PI) - PI;  // sbm.py:209
+        spatial[b] = e_y;
+        spatial[(size_t)B + b] = e_psi;
+    }
+    return __shfl_sync(0xffffffffu, w, 0);
+}
+
 __global__ void localize_t2s_kernel(const double* __restrict__ state, int* __restrict__ wp_id,
                                     double* __restrict__ spatial, int* __restrict__ flags, PathView pv, double length,
                                     int B) {
@@ -268,10 +294,13 @@ __device__ __noinline__ int close_segment(double ox, double oy, double res, int 
 // Ray table: the cell sequence of every waypoint's ray (static border cell -> static border cell) is a
 // property of the path and the grid geometry, not of the scenario.  It is built once (per set_path /
 // set_base_grid / compute_width) by walking skimage's line_aa order on the device, and the per-step kernel
-// replays it: entry = word offset in the grid (bits 5..25) | bit (0..4) | at-end flag (bit 26), layout
-// [cell][waypoint] so that the lanes of a warp (consecutive waypoints) read consecutive words.
+// replays it: entry = word offset in the grid (bits 6..31) | at-end flag (bit 5) | bit (0..4), layout
+// [cell][waypoint] so that the lanes of a warp (consecutive waypoints) read consecutive words.  Entries past a ray's
+// end repeat its last cell: replaying them is inert (an occupied cell cannot close a segment when no free cell is
+// pending, a free end cell closes a zero-length one that rp.py:510 discards), so the replay needs no per-cell
+// "is this lane still inside its ray" predicate.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kRayEnd = 1u << 26;
+constexpr uint32_t kRayEnd = 1u << 5;
 
 __global__ void build_ray_table_kernel(GridView g, PathView pv, uint32_t* __restrict__ cells, int* __restrict__ len,
                                        int max_len) {
@@ -282,14 +311,17 @@ __global__ void build_ray_table_kernel(GridView g, PathView pv, uint32_t* __rest
     w2m(g, bc[0], bc[1], ubx, uby);  // rp.py:478
     w2m(g, bc[2], bc[3], lbx, lby);  // rp.py:480
     int n = 0, bad = 0, first = 1;
+    uint32_t last = 0u;
     line_aa_walk(ubx, uby, lbx, lby, [&](int x, int y) {
         if (first) { first = 0; return true; }  // rp.py:494 skips the first emitted cell (quirk Q4)
         if (x < 0 || y < 0 || x >= g.W || y >= g.H || n >= max_len) { bad = 1; return false; }
         const uint32_t word = (uint32_t)(y * g.pitch_words + (x >> 5));
-        cells[(size_t)n * pv.n_wp + k] = (word << 5) | (uint32_t)(x & 31) | ((x == lbx && y == lby) ? kRayEnd : 0u);
+        last = (word << 6) | (uint32_t)(x & 31) | ((x == lbx && y == lby) ? kRayEnd : 0u);
+        cells[(size_t)n * pv.n_wp + k] = last;
         ++n;
         return true;
     });
+    for (int i = n; i < max_len; ++i) cells[(size_t)i * pv.n_wp + k] = last;
     len[k] = bad ? -1 : n;  // -1: the ray leaves the grid (IndexError in the reference, rp.py:496)
 }
 
@@ -300,40 +332,50 @@ void launch_build_ray_table(const GridView& g, const PathView& pv, uint32_t* cel
 
 // Replay one waypoint's ray over a bit grid and record its free segments (rp.py:494-518).
 // base[word] is the grid word (staged rows: base is pre-offset by the first staged row).
+// Per cell: v = its bit; term = occupied or at-end; a segment closes at a term cell when a free cell is pending
+// (rp.py:503-515); `uo` (the segment's upper end) moves to every term cell (rp.py:514 / 516-518).
 __device__ __forceinline__ int replay_ray(const uint32_t* __restrict__ base, const uint32_t* __restrict__ cells, int n_wp,
-                                          int k, int len, int max_len_warp, int ubx, int uby, int pitch, double ox,
-                                          double oy, double res, double min_width, short4* segs, uint32_t safe_word) {
+                                          int k, int max_len_warp, int ubx, int uby, int pitch, double ox, double oy,
+                                          double res, double min_width, short4* segs) {
     uint32_t uo = 0xffffffffu;  // packed cell of the segment's upper end; all ones = the ray's start cell
-    int free_cells = 0, nseg = 0;
+    uint32_t pending = 0u;      // bit 0: a free cell has been seen since the last close
+    int nseg = 0;
     const uint32_t* p = cells + k;
-    const uint32_t safe = safe_word << 5;  // predicated-off slots still load a grid word: keep it inside the staged rows
     constexpr int U = 8;
-    // all lanes run the warp's longest ray so that the loads stay converged; shorter rays are predicated off.
-    // U table entries and their grid words are fetched ahead of the (serial) segment state machine.
-    for (int i0 = 0; i0 < max_len_warp; i0 += U, p += (size_t)U * n_wp) {
+    // all lanes run the warp's longest ray so that the loads stay converged (shorter rays replay their padding).
+    // Software pipeline: the table entries of batch i+1 are in flight (L2 latency) while batch i's grid words are
+    // fetched from shared memory and its (serial) segment state machine runs.
+    uint32_t en[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) en[j] = __ldg(p + (size_t)j * n_wp);
+    for (int i0 = 0; i0 < max_len_warp; i0 += U) {
         uint32_t e[U], wv[U];
 #pragma unroll
-        for (int j = 0; j < U; ++j) e[j] = (i0 + j < len) ? __ldg(p + (size_t)j * n_wp) : safe;
+        for (int j = 0; j < U; ++j) e[j] = en[j];
+        p += (size_t)U * n_wp;
+        if (i0 + U < max_len_warp) {
 #pragma unroll
-        for (int j = 0; j < U; ++j) wv[j] = base[(e[j] >> 5) & 0x1fffffu];
+            for (int j = 0; j < U; ++j) en[j] = __ldg(p + (size_t)j * n_wp);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) wv[j] = base[e[j] >> 6];
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-            const bool active = i0 + j < len;
-            const uint32_t v = (wv[j] >> (e[j] & 31u)) & 1u;
-            free_cells |= (int)v & (int)active;
-            const bool closing = active & ((v == 0u) | ((e[j] & kRayEnd) != 0u)) & (free_cells != 0);
-            if (closing) {  // rp.py:503-515
-                const uint32_t w = (e[j] >> 5) & 0x1fffffu;
-                const int y = (int)(w / (uint32_t)pitch), x = (int)(w % (uint32_t)pitch) * 32 + (int)(e[j] & 31u);
+            const uint32_t x = __funnelshift_r(wv[j], 0u, e[j]);  // bit 0 = the cell's bit (shift count = e & 31)
+            const uint32_t term = (~x | (e[j] >> 5)) & 1u;         // occupied, or the ray's end cell
+            pending |= x;
+            if (term & pending) {  // rp.py:503-515
+                const uint32_t w = e[j] >> 6;
+                const int y = (int)(w / (uint32_t)pitch), xx = (int)(w % (uint32_t)pitch) * 32 + (int)(e[j] & 31u);
                 int ux = ubx, uy = uby;
                 if (uo != 0xffffffffu) {
-                    const uint32_t wu = (uo >> 5) & 0x1fffffu;
+                    const uint32_t wu = uo >> 6;
                     uy = (int)(wu / (uint32_t)pitch); ux = (int)(wu % (uint32_t)pitch) * 32 + (int)(uo & 31u);
                 }
-                nseg = close_segment(ox, oy, res, ux, uy, x, y, min_width, segs, nseg);
-                free_cells = 0;
+                nseg = close_segment(ox, oy, res, ux, uy, xx, y, min_width, segs, nseg);
+                pending = 0u;
             }
-            uo = (active & ((v == 0u) | closing)) ? e[j] : uo;  // rp.py:514 / 516-518
+            uo = term ? e[j] : uo;
         }
     }
     return nseg;
@@ -400,9 +442,7 @@ raycast_kernel(RaycastArgs a) {
         if (fl & (MPC_ST_DEAD | MPC_ST_FINISHED)) continue;
         int wp_now;
         if (a.state) {  // get_current_waypoint + t2s (sbm.py:256-279, 183-219), same arithmetic as localize_t2s_kernel
-            int w = -1;
-            if (lane == 0) w = localize_one(a.state, a.spatial_out, pv, a.length, b, a.B);
-            w = __shfl_sync(0xffffffffu, w, 0);
+            const int w = localize_warp(a.state, a.spatial_out, pv, a.length, b, a.B, lane);
             if (w < 0) {
                 if (lane == 0 && a.flags) atomicOr(&a.flags[b], MPC_ST_FINISHED);
                 continue;
@@ -439,8 +479,8 @@ raycast_kernel(RaycastArgs a) {
             const int max_len_warp = __reduce_max_sync(0xffffffffu, len);
             int ubx, uby;
             w2m(g, pv.border[4 * k], pv.border[4 * k + 1], ubx, uby);  // the ray's start cell (rp.py:478, 488)
-            const int nseg = replay_ray(base, a.ray_cells, pv.n_wp, k, len, max_len_warp, ubx, uby, g.pitch_words, g.ox,
-                                        g.oy, g.res, a.min_width, segs + (n < N ? n : 0) * kMaxSeg, (uint32_t)(row0 * g.pitch_words));
+            const int nseg = replay_ray(base, a.ray_cells, pv.n_wp, k, max_len_warp, ubx, uby, g.pitch_words, g.ox, g.oy,
+                                        g.res, a.min_width, segs + (n < N ? n : 0) * kMaxSeg);
             if (n < N) {
                 if (nseg > kMaxSeg) status |= MPC_ST_INDEX_ERROR;
                 nsegs[n] = nseg;
