@@ -160,6 +160,12 @@ int mpc_solve_qp(mpc_engine *h, const double *d_Pd, const double *d_q, const dou
                  const double *d_l, const double *d_u, double *d_x_out, int32_t *d_iters,
                  int32_t *d_qp_status, int32_t B);
 
+/* ---- MPC.update_prediction (MPC.py:224-248) + s2t (sbm.py:155-181), batched -------------------
+ * d_x_sol[B][5N+3]: solver output in dec.x order (mpc_assemble_solve's d_x_out); d_wp_id[B]: the waypoint each
+ * car is localised at; d_xy_out[B][N-2][2]: world x, y of the predicted stages 2 .. N-1 (NaN past the end of a
+ * non-circular path, where the reference exits). */
+int mpc_predict_xy(mpc_engine *h, const double *d_x_sol, const int32_t *d_wp_id, double *d_xy_out, int32_t B);
+
 /* ---- K4 back: BicycleModel.drive (sbm.py:221-244) ------------------------------------------ */
 int mpc_rollout(mpc_engine *h, double *d_state, const double *d_spatial, const int32_t *d_wp_id,
                 const double *d_u, const int32_t *d_flags, int32_t B);

@@ -185,6 +185,19 @@ class BatchedMPC(_MPCBase):
                            b.iters, b.qp_status, b.flags)
         return b.u
 
+    def update_prediction(self):
+        """MPC.update_prediction (MPC.py:224-248) for every scenario, on the device: (B, N-2, 2) tensor of the world
+        x / y of the predicted stages 2 .. N-1 of the last get_control(want_solution=True)."""
+        b, t = self._b, self._b.torch
+        if getattr(b, "xy_pred", None) is None:
+            b.xy_pred = t.zeros((self.B, max(self.N - 2, 0), 2), dtype=t.float64, device=b.x_sol.device)
+        self.engine.predict_xy(b.x_sol, b.wp_id, b.xy_pred)
+        return b.xy_pred
+
+    @property
+    def current_prediction(self):
+        return self.update_prediction()
+
     def run_closed_loop(self, max_steps):
         """max_steps x (get_control + drive) on engine-owned state (CUDA graph); returns the statistics
         dict and leaves the final state in the model's tensors."""

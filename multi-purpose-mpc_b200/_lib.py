@@ -40,7 +40,7 @@ EXPORTS = [
     "mpc_raycast", "mpc_update_path_constraints", "mpc_assemble_solve", "mpc_solve_qp", "mpc_rollout",
     "mpc_scenarios_init", "mpc_scenarios_set_state", "mpc_step", "mpc_run_closed_loop", "mpc_step_host",
     "mpc_scenarios_ptrs", "mpc_scenarios_read", "mpc_launch_count", "mpc_set_profiling", "mpc_get_profile",
-    "mpc_speed_profile",
+    "mpc_speed_profile", "mpc_predict_xy",
 ]
 
 _lib = None
@@ -256,6 +256,10 @@ class Engine:
     def solve_qp(self, Pd, q, Ax, l, u, x_out=None, iters=None, qp_status=None):
         _check(self.L.mpc_solve_qp(self.h, _ptr(Pd), _ptr(q), _ptr(Ax), _ptr(l), _ptr(u), _ptr(x_out), _ptr(iters),
                                    _ptr(qp_status), Pd.shape[0]))
+
+    def predict_xy(self, x_sol, wp_id, xy_out):
+        """MPC.update_prediction for every scenario: xy_out[B, N-2, 2] from the solver output x_sol[B, 5N+3]."""
+        _check(self.L.mpc_predict_xy(self.h, _ptr(x_sol), _ptr(wp_id), _ptr(xy_out), x_sol.shape[0]))
 
     def rollout(self, state, spatial, wp_id, u, flags=None):
         _check(self.L.mpc_rollout(self.h, _ptr(state), _ptr(spatial), _ptr(wp_id), _ptr(u), _ptr(flags),

@@ -256,7 +256,7 @@ int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* 
 int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings& st, const PathView& pv,
                           const double* spatial, const int* wp_id, double* control, const double* ub, const double* lb,
                           int* infeas, double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
-                          cudaStream_t s, double* rollout_state, double Ts) {
+                          cudaStream_t s, double* rollout_state, double Ts, const int* order) {
 #define WARP_GO(T_, L_) assemble_solve_launch<T_, L_, Tune<T_>::rlev, Tune<T_>::minb>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts)
 #define BLOCK_GO(T_, L_, NT_) assemble_solve_block_launch<T_, L_, NT_>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts)
     const int ns = mp.N + 1;
@@ -266,7 +266,7 @@ int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings
         else if (ns <= 64) BLOCK_GO(double, 6, 64); else BLOCK_GO(double, 7, 128);
     } else if (use_pair_kernels() && ns <= 64) {
         return launch_assemble_solve_pair(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status,
-                                          flags, B, s, rollout_state, Ts);
+                                          flags, B, s, rollout_state, Ts, order);
     } else {
         if (ns <= 16) WARP_GO(float, 4); else if (ns <= 32) WARP_GO(float, 5);
         else if (ns <= 64) BLOCK_GO(float, 6, 64); else BLOCK_GO(float, 7, 128);

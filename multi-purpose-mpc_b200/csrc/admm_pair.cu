@@ -116,10 +116,13 @@ assemble_solve_pair_kernel(MpcParams mp, AdmmSettings st, const f2 al2, const f2
                            const int* __restrict__ wp_id, double* __restrict__ control, const double* __restrict__ ub,
                            const double* __restrict__ lb, int* __restrict__ infeas, double* __restrict__ u_out,
                            double* __restrict__ x_out, int* __restrict__ iters, int* __restrict__ qp_status,
-                           int* __restrict__ flags, int B, double* __restrict__ rollout_state, double Ts) {
+                           int* __restrict__ flags, int B, double* __restrict__ rollout_state, double Ts,
+                           const int* __restrict__ order) {
     constexpr int G = 32 / LPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = (blockIdx.x * kPairWarpsPerBlock + warp) * G + lane / LPS;
+    const int slot = (blockIdx.x * kPairWarpsPerBlock + warp) * G + lane / LPS;
+    // `order` (closed-loop path): scenarios sorted by the length of their previous solve, see geometry.cu::plan_solve_order
+    const int b = slot < B ? (order ? order[slot] : slot) : B;
     const int fl = (b < B && flags) ? flags[b] : 0;
     const bool live = b < B && !(fl & (MPC_ST_DEAD | MPC_ST_FINISHED));
     if (!__any_sync(kFull, live)) return;
@@ -166,14 +169,15 @@ template <int LPS, bool LOOSE>
 static void assemble_solve_pair_launch(const MpcParams& mp, const AdmmSettings& st, const PathView& pv,
                                        const double* spatial, const int* wp_id, double* control, const double* ub,
                                        const double* lb, int* infeas, double* u_out, double* x_out, int* iters,
-                                       int* qp_status, int* flags, int B, cudaStream_t s, double* rs, double Ts) {
+                                       int* qp_status, int* flags, int B, cudaStream_t s, double* rs, double Ts,
+                                       const int* order) {
     constexpr int per_block = kPairWarpsPerBlock * (32 / LPS);
     const size_t smem = pair_smem_bytes<LPS>();
     cudaFuncSetAttribute(assemble_solve_pair_kernel<LPS, LOOSE, kPairMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem);
     assemble_solve_pair_kernel<LPS, LOOSE, kPairMinBlocks><<<(B + per_block - 1) / per_block, 32 * kPairWarpsPerBlock, smem, s>>>(
         mp, st, make_float2((float)st.alpha, (float)st.alpha), make_float2(-(float)st.alpha, -(float)st.alpha), pv, spatial, wp_id,
-        control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, rs, Ts);
+        control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, rs, Ts, order);
 }
 
 int launch_solve_qp_pair(int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax, const double* l,
@@ -189,14 +193,14 @@ int launch_solve_qp_pair(int N, const AdmmSettings& st, const double* Pd, const 
 int launch_assemble_solve_pair(const MpcParams& mp, const AdmmSettings& st, const PathView& pv, const double* spatial,
                                const int* wp_id, double* control, const double* ub, const double* lb, int* infeas,
                                double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B, cudaStream_t s,
-                               double* rollout_state, double Ts) {
+                               double* rollout_state, double Ts, const int* order) {
     const int ns = mp.N + 1;
     if (ns > 64) return MPC_E_UNSUPPORTED;
     // e_psi and t unbounded (the reference's StateConstraints): OSQP's "loose" rows, skipped by the loop
     const bool loose = mp.xmin[1] <= -kOsqpInfty && mp.xmax[1] >= kOsqpInfty && mp.xmin[2] <= -kOsqpInfty &&
                        mp.xmax[2] >= kOsqpInfty;
-#define PAIR_GO(LPS_) do { if (loose) assemble_solve_pair_launch<LPS_, true>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts); \
-                           else assemble_solve_pair_launch<LPS_, false>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts); } while (0)
+#define PAIR_GO(LPS_) do { if (loose) assemble_solve_pair_launch<LPS_, true>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts, order); \
+                           else assemble_solve_pair_launch<LPS_, false>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts, order); } while (0)
     if (ns <= 16) PAIR_GO(8); else if (ns <= 32) PAIR_GO(16); else PAIR_GO(32);
 #undef PAIR_GO
     return 0;

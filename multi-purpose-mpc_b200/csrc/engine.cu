@@ -1,5 +1,6 @@
 // engine.cu -- the C ABI of libmpc_b200.so (include/mpc_b200.h): handle, tables, launches, CUDA graph.
 #include "engine.h"
+#include <cstdlib>
 
 #include <cmath>
 #include <cstdio>
@@ -70,6 +71,7 @@ struct mpc_engine {
     int B = 0;
     DevBuf<double> s_state, s_spatial, s_control, s_ub, s_lb, s_u, s_acc;
     DevBuf<int> s_wp_id, s_iters, s_qp_status, s_flags, s_infeas;
+    DevBuf<int> s_order;  // solve order of the closed-loop step (geometry.cu::plan_solve_order)
     cudaGraphExec_t graph_exec = nullptr;
     int graph_B = 0;
     // pinned staging for mpc_step_host
@@ -79,6 +81,7 @@ struct mpc_engine {
     int pin_B = 0;
     // profiling
     int profiling = 0;
+    int no_solve_order = 0;  // MPC_SOLVE_ORDER=off: scenarios are solved in index order (A/B switch)
     double prof_ms[4] = {0, 0, 0, 0};
     int64_t prof_launches[4] = {0, 0, 0, 0};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -148,6 +151,10 @@ int mpc_engine_create(const mpc_config* cfg, mpc_engine** out) {
     h->cfg = *cfg;
     refresh_params(h);
     if (h->d_err.alloc(1) != cudaSuccess) { delete h; return fail(MPC_E_CUDA, "cudaMalloc failed"); }
+    {
+        const char* e2 = getenv("MPC_SOLVE_ORDER");
+        h->no_solve_order = (e2 && e2[0] == 'o' && e2[1] == 'f') ? 1 : 0;
+    }
     cudaMemset(h->d_err.p, 0, sizeof(int));
     for (int i = 0; i < 5; ++i) cudaEventCreate(&h->ev[i]);
     *out = h;
@@ -162,7 +169,7 @@ int mpc_engine_destroy(mpc_engine* h) {
     h->d_obs_off.release(); h->d_rowspan.release(); h->d_err.release(); h->d_ray_cells.release(); h->d_ray_len.release();
     h->s_state.release(); h->s_spatial.release(); h->s_control.release(); h->s_ub.release(); h->s_lb.release();
     h->s_u.release(); h->s_acc.release(); h->s_wp_id.release(); h->s_iters.release(); h->s_qp_status.release();
-    h->s_flags.release(); h->s_infeas.release();
+    h->s_flags.release(); h->s_infeas.release(); h->s_order.release();
     if (h->pin_state) cudaFreeHost(h->pin_state);
     if (h->pin_u) cudaFreeHost(h->pin_u);
     if (h->pin_flags) cudaFreeHost(h->pin_flags);
@@ -467,6 +474,16 @@ int mpc_rollout(mpc_engine* h, double* d_state, const double* d_spatial, const i
     return 0;
 }
 
+int mpc_predict_xy(mpc_engine* h, const double* d_x_sol, const int32_t* d_wp_id, double* d_xy_out, int32_t B) {
+    if (int r = need(h, false, false)) return r;
+    if (!d_x_sol || !d_wp_id || !d_xy_out) return fail(MPC_E_INVALID, "null argument");
+    if (B <= 0 || h->cfg.N <= 2) return 0;
+    launch_predict_xy(d_x_sol, d_wp_id, h->pv, h->cfg.N, d_xy_out, B, h->stream);
+    ++h->launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // engine-owned scenarios
 // ---------------------------------------------------------------------------------------------
@@ -487,6 +504,7 @@ int mpc_scenarios_init(mpc_engine* h, const double* h_state, int32_t B) {
     CUDA_OK(h->s_qp_status.alloc(B));
     CUDA_OK(h->s_flags.alloc(B));
     CUDA_OK(h->s_infeas.alloc(B));
+    CUDA_OK(h->s_order.alloc(B));
     h->B = B;
     drop_graph(h);
     return mpc_scenarios_set_state(h, h_state, nullptr, nullptr);
@@ -526,12 +544,14 @@ static int enqueue_step(mpc_engine* h, bool with_stats, bool timed) {
     const uint32_t* grids = h->grids_B ? h->d_grids.p : h->d_base.p;
     const size_t stride = h->grids_B ? (size_t)h->words : 0;
     if (!timed) {
+        // the solve order is planned by one extra CTA of the raycast launch from the previous step's iteration counts
+        int* order = (h->cfg.precision == 0 && B <= (1 << 16) && !h->no_solve_order) ? h->s_order.p : nullptr;
         launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->d_ray_cells.p, h->d_ray_len.p, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm,
                        h->s_ub.p, h->s_lb.p, nullptr, h->s_flags.p, B, h->rowspan_valid, s, h->s_state.p, h->s_wp_id.p,
-                       h->s_spatial.p, h->length);
+                       h->s_spatial.p, h->length, h->s_iters.p, order);
         int r = launch_assemble_solve(h->cfg.precision, h->mp, h->st, h->pv, h->s_spatial.p, h->s_wp_id.p, h->s_control.p,
                                       h->s_ub.p, h->s_lb.p, h->s_infeas.p, h->s_u.p, nullptr, h->s_iters.p,
-                                      h->s_qp_status.p, h->s_flags.p, B, s, h->s_state.p, h->cfg.Ts);
+                                      h->s_qp_status.p, h->s_flags.p, B, s, h->s_state.p, h->cfg.Ts, order);
         if (r) return fail(r, "unsupported horizon");
         // the rollout only touches `state`; flags / iters / e_y of this step are final, so the statistics can follow it
         if (with_stats) launch_accumulate_stats(h->s_flags.p, h->s_iters.p, h->s_spatial.p, h->s_acc.p, B, s);

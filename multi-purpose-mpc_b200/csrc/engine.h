@@ -26,11 +26,13 @@ void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridV
                     const int2* rowspan, int max_rows, const uint32_t* ray_cells, const int* ray_len, const int* wp_id, int first_offset, int N, double min_width,
                     double sm, double* ub, double* lb, double* cells_sm, int* flags, int B, bool rowspan_ok,
                     cudaStream_t st, const double* state = nullptr, int* wp_id_out = nullptr,
-                    double* spatial_out = nullptr, double length = 0.0);
+                    double* spatial_out = nullptr, double length = 0.0, const int* prev_iters = nullptr,
+                    int* order_out = nullptr);
 void launch_localize(const double* state, int* wp_id, double* spatial, int* flags, const PathView& pv, double length,
                      int B, cudaStream_t st);
 void launch_rollout(double* state, const double* spatial, const int* wp_id, const double* u, const int* flags,
                     const PathView& pv, double L, double Ts, int B, cudaStream_t st);
+void launch_predict_xy(const double* x_sol, const int* wp_id, const PathView& pv, int N, double* xy, int B, cudaStream_t st);
 void launch_accumulate_stats(const int* flags, const int* iters, const double* spatial, double* acc, int B,
                              cudaStream_t st);
 
@@ -40,7 +42,7 @@ int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* 
 int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings& st, const PathView& pv,
                           const double* spatial, const int* wp_id, double* control, const double* ub, const double* lb,
                           int* infeas, double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
-                          cudaStream_t s, double* rollout_state = nullptr, double Ts = 0.0);
+                          cudaStream_t s, double* rollout_state = nullptr, double Ts = 0.0, const int* order = nullptr);
 
 // admm_pair.cu (fp32, N + 1 <= 64)
 int launch_solve_qp_pair(int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax, const double* l,
@@ -48,6 +50,6 @@ int launch_solve_qp_pair(int N, const AdmmSettings& st, const double* Pd, const 
 int launch_assemble_solve_pair(const MpcParams& mp, const AdmmSettings& st, const PathView& pv, const double* spatial,
                                const int* wp_id, double* control, const double* ub, const double* lb, int* infeas,
                                double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B, cudaStream_t s,
-                               double* rollout_state, double Ts);
+                               double* rollout_state, double Ts, const int* order);
 
 }  // namespace mpcb

@@ -401,7 +401,38 @@ struct RaycastArgs {
     int* wp_id_out;
     double* spatial_out;
     double length;
+    // solve order for this step (closed-loop path; nullptr = off): one extra CTA of the launch buckets the scenarios by
+    // the ADMM iteration count of their previous solve, longest first (see plan_solve_order)
+    const int* prev_iters;
+    int* order_out;
 };
+
+// Solve order for the paired ADMM kernel.  Its warps hold 2-4 scenarios that run in lockstep until the slowest is
+// done, and CTAs are dispatched in index order; the iteration count of a car's previous solve predicts the next one
+// well (the hard stretches of the track stay hard for several steps), so the scenarios are bucketed by it
+// (25 iterations per bucket = one termination check), longest first: warp-mates get similar iteration counts and
+// the long solves start first (shorter tail).  One CTA, shared-memory counting sort; the order inside a bucket is
+// arbitrary, which cannot change any result: a scenario's arithmetic never depends on its warp-mates.
+__device__ void plan_solve_order(const int* __restrict__ prev_iters, const int* __restrict__ flags, int* __restrict__ order,
+                                 int B) {
+    constexpr int NB = 192;  // 25 iterations per bucket: covers OSQP's default max_iter = 4000
+    __shared__ int hist[NB], cursor[NB];
+    for (int i = threadIdx.x; i < NB; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    auto bucket = [&](int b) {
+        if (flags && (flags[b] & (MPC_ST_DEAD | MPC_ST_FINISHED))) return NB - 1;  // skipped by the solve: last
+        const int k = prev_iters[b] / 25;
+        return NB - 1 - (k < NB - 1 ? k : NB - 1);
+    };
+    for (int b = threadIdx.x; b < B; b += blockDim.x) atomicAdd(&hist[bucket(b)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < NB; ++i) { cursor[i] = run; run += hist[i]; }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) order[atomicAdd(&cursor[bucket(b)], 1)] = b;
+}
 
 // MODE 0: no staging (global / L1 reads).  MODE 1: one grid shared by all scenarios, staged once per CTA
 // (whole grid, one TMA bulk copy) and reused by all warps and all scenarios the CTA loops over.
@@ -413,6 +444,11 @@ raycast_kernel(RaycastArgs a) {
     const GridView& g = a.g;
     const PathView& pv = a.pv;
     const int N = a.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int ray_ctas = a.order_out ? (int)gridDim.x - 1 : (int)gridDim.x;
+    if ((int)blockIdx.x == ray_ctas) {  // the extra CTA: plans the solve order while the others walk rays
+        plan_solve_order(a.prev_iters, a.flags, a.order_out, a.B);
+        return;
+    }
     // shared layout: [mbarriers: 8 x u64][staging slabs][per-warp scratch: segs, prev_cells, nsegs]
     uint64_t* mbars = reinterpret_cast<uint64_t*>(smem_raw);
     uint32_t* stage = reinterpret_cast<uint32_t*>(smem_raw + 128);
@@ -437,7 +473,7 @@ raycast_kernel(RaycastArgs a) {
         __syncwarp();
     }
     uint32_t phase = 0;
-    for (int b = blockIdx.x * nwarps + warp; b < a.B; b += gridDim.x * nwarps) {
+    for (int b = blockIdx.x * nwarps + warp; b < a.B; b += ray_ctas * nwarps) {
         const int fl = a.flags ? a.flags[b] : 0;
         if (fl & (MPC_ST_DEAD | MPC_ST_FINISHED)) continue;
         int wp_now;
@@ -610,8 +646,10 @@ int raycast_plan(const GridView& g, int N, bool shared_grid, int max_rows, bool 
 void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridView& g, const PathView& pv,
                     const int2* rowspan, int max_rows, const uint32_t* ray_cells, const int* ray_len, const int* wp_id, int first_offset, int N, double min_width,
                     double sm, double* ub, double* lb, double* cells_sm, int* flags, int B, bool rowspan_ok,
-                    cudaStream_t st, const double* state, int* wp_id_out, double* spatial_out, double length) {
+                    cudaStream_t st, const double* state, int* wp_id_out, double* spatial_out, double length,
+                    const int* prev_iters, int* order_out) {
     RaycastArgs a;
+    a.prev_iters = prev_iters; a.order_out = order_out;
     a.state = state; a.wp_id_out = wp_id_out; a.spatial_out = spatial_out; a.length = length;
     a.grids = grids; a.grid_stride_words = grid_stride_words; a.g = g; a.pv = pv; a.rowspan = rowspan; a.wp_id = wp_id;
     a.ray_cells = ray_cells; a.ray_len = ray_len;
@@ -624,7 +662,7 @@ void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridV
     const int ctas_needed = (B + warps - 1) / warps;
     // persistent-style grid: enough CTAs to fill the machine a few times over, each looping over scenarios
     const int max_ctas = 148 * 8;
-    const int grid = ctas_needed < max_ctas ? ctas_needed : max_ctas;
+    const int grid = (ctas_needed < max_ctas ? ctas_needed : max_ctas) + (order_out ? 1 : 0);
     if (mode == 1) {
         cudaFuncSetAttribute(raycast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         raycast_kernel<1><<<grid, warps * 32, smem, st>>>(a);
@@ -675,6 +713,33 @@ void launch_rollout(double* state, const double* spatial, const int* wp_id, cons
 // ------------------------------------------------------------------------------------------------
 // closed-loop statistics: per-scenario accumulation + final reduction
 // ------------------------------------------------------------------------------------------------
+// MPC.update_prediction (MPC.py:224-248) + SpatialBicycleModel.s2t (sbm.py:155-181) for every scenario: the predicted
+// spatial states of stages 2 .. N-1 mapped back to world x / y about the horizon waypoints.  One thread per
+// (scenario, stage); x_sol is the solver output in the reference's dec.x order.
+__global__ void predict_xy_kernel(const double* __restrict__ x_sol, const int* __restrict__ wp_id, PathView pv, int N,
+                                  double* __restrict__ xy, int B) {
+    const int per = N - 2;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (per <= 0 || i >= (long)B * per) return;
+    const int b = (int)(i / per), n = 2 + (int)(i % per);
+    const long w = (long)wp_id[b] + n;
+    double x = NAN, y = NAN;
+    if (pv.circular || w < pv.n_wp) {  // rp.py:356-371: a non-circular path ends (the reference exits there)
+        const int k = (int)(w % pv.n_wp);
+        const double e_y = x_sol[(size_t)b * (5 * N + 3) + 3 * n];
+        x = pv.x[k] - e_y * pv.sin_psi[k];  // sbm.py:171
+        y = pv.y[k] + e_y * pv.cos_psi[k];  // sbm.py:172
+    }
+    xy[2 * i] = x;
+    xy[2 * i + 1] = y;
+}
+
+void launch_predict_xy(const double* x_sol, const int* wp_id, const PathView& pv, int N, double* xy, int B, cudaStream_t st) {
+    const long n = (long)B * (N - 2);
+    if (n <= 0) return;
+    predict_xy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_sol, wp_id, pv, N, xy, B);
+}
+
 __global__ void accumulate_stats_kernel(const int* __restrict__ flags, const int* __restrict__ iters,
                                         const double* __restrict__ spatial, double* __restrict__ acc /*[4][B]*/, int B) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;

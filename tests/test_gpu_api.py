@@ -93,6 +93,16 @@ def test_batched_api_matches_single_car(sim, track):
         assert tuple(u.shape) == (B, 2)
         assert torch.equal(u[0], u[B - 1])                                     # identical scenarios, identical answers
         assert np.abs(u[0].cpu().numpy() - C1["u"][k]).max() <= 1e-6
+    # MPC.update_prediction, batched: same numbers as the single-car host method (MPC.py:224-248, sbm.py:155-181)
+    xy = bm.update_prediction().cpu().numpy()
+    assert xy.shape == (B, 28, 2)
+    xs = bm.solution[0].cpu().numpy()
+    wp0 = int(bm._b.wp_id[0].item())
+    for n in range(2, 30):
+        wp = rp.get_waypoint(wp0 + n)
+        e_y = xs[3 * n]
+        assert xy[0, n - 2, 0] == wp.x - e_y * np.sin(wp.psi) and xy[0, n - 2, 1] == wp.y + e_y * np.cos(wp.psi)
+    assert np.array_equal(xy[0], xy[B - 1])
     stats = bm.run_closed_loop(10)
     assert stats["scenario_steps"] == 10 * B and stats["dead"] == 0
     assert np.abs(cars.s.cpu().numpy() - C1["state_after"][12][3]).max() <= 1e-6
