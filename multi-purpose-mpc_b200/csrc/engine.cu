@@ -25,6 +25,7 @@ static int fail(int code, const std::string& msg) {
 template <typename T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    bool owned = true;
     cudaError_t alloc(size_t count) {
         if (count <= n && p) return cudaSuccess;
         release();
@@ -32,10 +33,15 @@ template <typename T> struct DevBuf {
         if (e == cudaSuccess) n = count;
         return e;
     }
+    void view(T* ptr, size_t count) {  // a window into another allocation (not freed here)
+        release();
+        p = ptr; n = count; owned = false;
+    }
     void release() {
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
         p = nullptr;
         n = 0;
+        owned = true;
     }
 };
 
@@ -69,6 +75,7 @@ struct mpc_engine {
     DevBuf<int> d_err;
     // scenarios (engine-owned closed loop)
     int B = 0;
+    DevBuf<double> s_io;  // [state 4B | u 2B | flags B (int)]: what mpc_step_host returns, one D2H copy
     DevBuf<double> s_state, s_spatial, s_control, s_ub, s_lb, s_u, s_acc;
     DevBuf<int> s_wp_id, s_iters, s_qp_status, s_flags, s_infeas;
     DevBuf<int> s_order;  // solve order of the closed-loop step (geometry.cu::plan_solve_order)
@@ -169,10 +176,8 @@ int mpc_engine_destroy(mpc_engine* h) {
     h->d_obs_off.release(); h->d_rowspan.release(); h->d_err.release(); h->d_ray_cells.release(); h->d_ray_len.release();
     h->s_state.release(); h->s_spatial.release(); h->s_control.release(); h->s_ub.release(); h->s_lb.release();
     h->s_u.release(); h->s_acc.release(); h->s_wp_id.release(); h->s_iters.release(); h->s_qp_status.release();
-    h->s_flags.release(); h->s_infeas.release(); h->s_order.release();
-    if (h->pin_state) cudaFreeHost(h->pin_state);
-    if (h->pin_u) cudaFreeHost(h->pin_u);
-    if (h->pin_flags) cudaFreeHost(h->pin_flags);
+    h->s_flags.release(); h->s_infeas.release(); h->s_order.release(); h->s_io.release();
+    if (h->pin_state) cudaFreeHost(h->pin_state);  // pin_u / pin_flags point into it
     for (int i = 0; i < 5; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
     return 0;
@@ -492,17 +497,18 @@ int mpc_scenarios_init(mpc_engine* h, const double* h_state, int32_t B) {
     if (B <= 0 || !h_state) return fail(MPC_E_INVALID, "bad scenario arguments");
     if (h->grids_B && B > h->grids_B) return fail(MPC_E_INVALID, "B exceeds the number of scenario grids");
     const int N = h->cfg.N;
-    CUDA_OK(h->s_state.alloc(4 * (size_t)B));
+    CUDA_OK(h->s_io.alloc(6 * (size_t)B + ((size_t)B + 1) / 2));
+    h->s_state.view(h->s_io.p, 4 * (size_t)B);
+    h->s_u.view(h->s_io.p + 4 * (size_t)B, 2 * (size_t)B);
+    h->s_flags.view(reinterpret_cast<int*>(h->s_io.p + 6 * (size_t)B), (size_t)B);
     CUDA_OK(h->s_spatial.alloc(2 * (size_t)B));
     CUDA_OK(h->s_control.alloc(2 * (size_t)N * B));
     CUDA_OK(h->s_ub.alloc((size_t)N * B));
     CUDA_OK(h->s_lb.alloc((size_t)N * B));
-    CUDA_OK(h->s_u.alloc(2 * (size_t)B));
     CUDA_OK(h->s_acc.alloc(5 * (size_t)B));
     CUDA_OK(h->s_wp_id.alloc(B));
     CUDA_OK(h->s_iters.alloc(B));
     CUDA_OK(h->s_qp_status.alloc(B));
-    CUDA_OK(h->s_flags.alloc(B));
     CUDA_OK(h->s_infeas.alloc(B));
     CUDA_OK(h->s_order.alloc(B));
     h->B = B;
@@ -683,22 +689,20 @@ int mpc_step_host(mpc_engine* h, double* h_state, double* h_u_out, int32_t* h_fl
     if (int r = need(h, true, true)) return r;
     if (!h_state || !h_u_out) return fail(MPC_E_INVALID, "null host pointer");
     const int B = h->B;
+    const size_t io_bytes = 6 * (size_t)B * sizeof(double) + (size_t)B * sizeof(int);
     if (h->pin_B < B) {
         if (h->pin_state) cudaFreeHost(h->pin_state);
-        if (h->pin_u) cudaFreeHost(h->pin_u);
-        if (h->pin_flags) cudaFreeHost(h->pin_flags);
-        CUDA_OK(cudaMallocHost(&h->pin_state, 4 * (size_t)B * sizeof(double)));
-        CUDA_OK(cudaMallocHost(&h->pin_u, 2 * (size_t)B * sizeof(double)));
-        CUDA_OK(cudaMallocHost(&h->pin_flags, (size_t)B * sizeof(int)));
+        CUDA_OK(cudaMallocHost(&h->pin_state, io_bytes));
+        h->pin_u = h->pin_state + 4 * (size_t)B;
+        h->pin_flags = reinterpret_cast<int*>(h->pin_state + 6 * (size_t)B);
         h->pin_B = B;
     }
     cudaStream_t s = h->stream;
     memcpy(h->pin_state, h_state, 4 * (size_t)B * sizeof(double));
     CUDA_OK(cudaMemcpyAsync(h->s_state.p, h->pin_state, 4 * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, s));
     if (int r = enqueue_step(h, false, false)) return r;
-    CUDA_OK(cudaMemcpyAsync(h->pin_state, h->s_state.p, 4 * (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaMemcpyAsync(h->pin_u, h->s_u.p, 2 * (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaMemcpyAsync(h->pin_flags, h->s_flags.p, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    // state | u | flags are one device allocation (s_io): one device-to-host copy
+    CUDA_OK(cudaMemcpyAsync(h->pin_state, h->s_io.p, io_bytes, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
     memcpy(h_state, h->pin_state, 4 * (size_t)B * sizeof(double));
     memcpy(h_u_out, h->pin_u, 2 * (size_t)B * sizeof(double));
