@@ -131,7 +131,7 @@ def run_reference(args, rank, world):
         return
     T, grid = load_track()
     B = args.batch
-    sample = min(B, 1024)
+    sample = B  # every timed step = one closed-loop step of the whole per-GPU batch on the host cores
     states = scenario_states(T, B, 0, sample)
     for _ in range(max(args.warmup, 0) and 1):
         time_cpu_port(T, grid, states[:, :64], 1)
@@ -164,7 +164,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="scenarios per GPU")
     ap.add_argument("--precision", type=int, default=0, help="0 = fp32 ADMM (production), 1 = fp64")
-    ap.add_argument("--cpu-sample", type=int, default=768, help="cars in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="cars in the CPU-baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="host time spent on the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="tracking", choices=["tracking", "obstacles"],
                     help="tracking = BASELINE configs[1] (headline); obstacles = configs[2] style: per-scenario random "
@@ -323,11 +324,20 @@ def main():
     # ---------------- CPU baseline: the oracle port on a bounded sample, rank 0, N = 1 only --------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and obstacles is None:
+        # bounded sample: the whole batch, closed loop, for about args.cpu_seconds of host time (chunks of 8 steps)
         sample = min(args.cpu_sample, B)
-        v, dt, nthr, _ = time_cpu_port(T, grid, states[:, :sample], 2)
-        cpu = {"value": v, "unit": UNIT, "cores": nthr, "kind": "port",
-               "sample": "%d of the %d cars x 2 closed-loop steps (%.1f s), oracle/*.c fp64, OpenMP over cars"
-                         % (sample, B, dt)}
+        orc_, world_ = cpu_oracle_world(T, grid)
+        st_ = np.ascontiguousarray(states[:, :sample].T.copy())
+        ctrl_ = np.zeros((sample, 2 * N_HORIZON)); inf_ = np.zeros(sample, np.int32); alive_ = np.ones(sample, np.int32)
+        nthr = orc_.num_threads()
+        solves, nsteps, t0 = 0.0, 0, time.perf_counter()
+        while time.perf_counter() - t0 < args.cpu_seconds and nsteps < 2000:
+            stt = world_.batch_closed_loop(grid, st_, ctrl_, inf_, alive_, 8, nthr)
+            solves += stt[1]; nsteps += 8
+        dt = time.perf_counter() - t0
+        cpu = {"value": solves / dt, "unit": UNIT, "cores": nthr, "kind": "port",
+               "sample": "%d of the %d cars x %d closed-loop steps (%.1f s of host time, %d QP solves), oracle/*.c fp64, "
+                         "OpenMP over cars" % (sample, B, nsteps, dt, int(solves))}
 
     if rank == 0:
         line = {
