@@ -8,6 +8,8 @@ Bars (BASELINE.json north_star):
                                  fp32 path at the reference's own eps = 1e-3; identical status / iteration count
   rollout                      : <= 1e-6 relative over one lap given identical controls
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -352,7 +354,7 @@ def test_other_horizons_full_step(engine_factory, track, orc, orc_path, N, preci
         assert r["wp_id"] == o["wp_id"][b]
         assert np.array_equal(r["ub"], o["ub"][b]) and np.array_equal(r["lb"], o["lb"][b])
         assert r["qp_status"] == o["qp_status"][b], (b, r["qp_status"], o["qp_status"][b])
-        if precision == 1 or N <= 31:
+        if precision == 1 or r["qp_status"] == 1:  # fp32 may flag an infeasible QP a check earlier / later
             assert r["iters"] == o["iters"][b], (b, r["iters"], o["iters"][b])
         tol = 1e-7 if precision == 1 else QP_TOL
         assert np.abs(r["u"] - o["u"][b]).max() <= tol
@@ -456,3 +458,66 @@ def test_dead_and_finished_scenarios_are_skipped(engine_factory, track):
     assert np.array_equal(o["state"][:, 0], st[:, 0])          # frozen
     assert o["flags"][1] == 0 and o["state"][3, 1] > st[3, 1]   # the healthy neighbour drove on
     assert o["flags"][2] & mpc_b200.ST_FINISHED and np.array_equal(o["state"][:, 2], st[:, 2])
+
+
+# ------------------------------------------------------------------ kernel variants and scheduling -----------
+_VARIANT_CODE = r"""
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.environ["MPC_REPO"]); sys.path.insert(0, os.path.join(os.environ["MPC_REPO"], "tests"))
+import mpc_b200
+from mpc_b200 import _lib
+from conftest import Track, load_golden
+T = Track()
+TF = load_golden("teacher_forced.npz")
+B = 512
+rng = np.random.default_rng(11)
+st0 = np.repeat(TF["state"][:32], B // 32, axis=0)
+st0[:, 0] += rng.uniform(-0.002, 0.002, B); st0[:, 1] += rng.uniform(-0.002, 0.002, B)
+eng = mpc_b200.Engine(precision=0)
+eng.set_path(_lib.path_table(T.wp_x, T.wp_y, T.wp_psi, T.wp_kappa, T.wp_vref), T.length_cum, T.border, True)
+eng.set_base_grid(T.grid_obs, T.origin, T.res)
+eng.scenarios_init(np.ascontiguousarray(st0.T))
+iters, stats = [], []
+for k in range(12):
+    eng.step()
+    o = eng.scenarios_read()
+    iters.append(o["iters"].copy()); stats.append(o["qp_status"].copy())
+np.savez(os.environ["MPC_OUT"], state=o["state"], u=o["u"], control=o["control"], flags=o["flags"], iters=np.array(iters),
+         qp_status=np.array(stats))
+eng.close()
+"""
+
+
+def _run_variant(tmp_path, name, **env):
+    import subprocess, sys
+    out = str(tmp_path / (name + ".npz"))
+    e = dict(os.environ)
+    e.update(env)
+    e["MPC_REPO"] = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e["MPC_OUT"] = out
+    r = subprocess.run([sys.executable, "-c", _VARIANT_CODE], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return np.load(out)
+
+
+def test_solve_order_and_kernel_variant_do_not_change_the_answers(tmp_path):
+    """12 closed-loop steps of 512 cars (obstacle map, incl. infeasible QPs and fallbacks):
+    (a) planning the solve order from the previous step's iteration counts (which changes which scenarios share a
+        warp) must not change a single bit -- a scenario's arithmetic never depends on its warp-mates;
+    (b) the paired-stage and the lane-per-stage fp32 kernels are different roundings of the same OSQP iteration:
+        identical iteration counts where OSQP solves, controls within the fp32 tolerance."""
+    a = _run_variant(tmp_path, "pair_ordered")
+    b = _run_variant(tmp_path, "pair_unordered", MPC_SOLVE_ORDER="off")
+    for k in ("state", "u", "control", "flags", "iters", "qp_status"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    c = _run_variant(tmp_path, "stage", MPC_ADMM_KERNEL="stage")
+    assert np.array_equal(a["flags"], c["flags"]) and np.array_equal(a["qp_status"], c["qp_status"])
+    solved = a["qp_status"] == 1
+    assert solved.mean() > 0.8
+    # wherever OSQP solves, the two kernels take the same number of iterations in all 12 steps; a primal-infeasible QP
+    # (status -3 in both) may be certified a few checks earlier or later (fp32 round-off after 300+ passes, DESIGN 8)
+    assert np.array_equal(a["iters"][solved], c["iters"][solved])
+    assert float((a["iters"] == c["iters"]).mean()) > 0.9
+    assert np.abs(a["u"] - c["u"]).max() <= QP_TOL
+    assert np.abs(a["state"] - c["state"]).max() <= QP_TOL

@@ -123,3 +123,23 @@ def test_kernel_model_matches_oracle(orc, dtype, eps, tol):
         assert g["status"] == sto[j] and g["iter"] == ito[j]
         if sto[j] == 1 and g["status"] == 1:
             assert np.abs(g["x"] - xo[j]).max() < tol
+
+
+@pytest.mark.parametrize("dtype,eps,tol", [(np.float64, 1e-5, 1e-4), (np.float32, 1e-3, 1.5e-3)])
+def test_paired_vform_model_matches_oracle(orc, dtype, eps, tol):
+    """tools/admm_pcr_model.py::admm_vform with the paired factorisation (two stages per lane: in-lane cyclic reduction
+    + PCR over the odd stages) -- the blueprint of csrc/admm_pair.cuh -- against oracle/osqp_oracle.c: same status and
+    iteration count (incl. the infeasible rows 7 and 23), solution within the fp tolerance."""
+    from tools import admm_pcr_model as M
+    TF = load_golden("teacher_forced.npz")
+    Ap, Ai = fixed_pattern(30)
+    ks = [0, 7, 11, 23, 30]
+    xo, ito, sto = orc.batch_qp_solve(30, TF["qp_Pd"][ks], TF["qp_q"][ks], Ap, Ai, TF["qp_Ax"][ks], TF["qp_l"][ks],
+                                      TF["qp_u"][ks], eps_abs=eps, eps_rel=eps)
+    for j, k in enumerate(ks):
+        g = M.admm_vform(30, TF["qp_Pd"][k], TF["qp_q"][k], TF["qp_Ax"][k], TF["qp_l"][k], TF["qp_u"][k], dtype=dtype,
+                         eps_abs=eps, eps_rel=eps, paired=True)
+        if sto[j] in (1, -3):
+            assert g["status"] == sto[j] and g["iter"] == ito[j], (k, sto[j], ito[j], g["status"], g["iter"])
+        if sto[j] == 1 and g["status"] == 1:
+            assert np.abs(g["x"] - xo[j]).max() < tol
