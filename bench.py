@@ -237,6 +237,8 @@ def main():
     sampler.stop_flag = True
     launches = eng.launch_count() - l0
     ms_steps = [a.elapsed_time(b) for a, b in ev]
+    if os.environ.get("MPC_BENCH_VERBOSE"):
+        print("per-step ms:", ["%.3f" % v for v in ms_steps], file=sys.stderr)
     ms_total = D.max_over_ranks(float(np.sum(ms_steps)))
     out = eng.scenarios_read()
     iters_last = out["iters"].astype(np.int64)

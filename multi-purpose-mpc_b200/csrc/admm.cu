@@ -232,6 +232,26 @@ static bool use_pair_kernels() {
     }();
     return v;
 }
+// MPC_ADMM_KERNEL=pair pins the paired kernels (no per-step choice by the engine's long-solve heuristic)
+static bool force_pair_kernels() {
+    static const bool v = [] {
+        const char* e = getenv("MPC_ADMM_KERNEL");
+        return e && e[0] == 'p';
+    }();
+    return v;
+}
+
+// CUDA loads a kernel's code on its first launch (lazy loading, ~15 ms): touch both fp32 solve kernels of this horizon
+// up front so that the engine's per-step choice between them never pays that inside a control step.
+void preload_solve_kernels(int precision, int N) {
+    if (precision != 0) return;
+    const int ns = N + 1;
+    cudaFuncAttributes fa;
+    if (ns <= 16) cudaFuncGetAttributes(&fa, assemble_solve_kernel<float, 4, clamp_rlev<4, Tune<float>::rlev>(), Tune<float>::minb>);
+    else if (ns <= 32) cudaFuncGetAttributes(&fa, assemble_solve_kernel<float, 5, clamp_rlev<5, Tune<float>::rlev>(), Tune<float>::minb>);
+    preload_pair_kernels(N);
+    (void)cudaGetLastError();
+}
 
 int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax,
                     const double* l, const double* u, double* x_out, int* iters, int* status, int B, cudaStream_t s) {
@@ -256,7 +276,7 @@ int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* 
 int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings& st, const PathView& pv,
                           const double* spatial, const int* wp_id, double* control, const double* ub, const double* lb,
                           int* infeas, double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
-                          cudaStream_t s, double* rollout_state, double Ts, const int* order) {
+                          cudaStream_t s, double* rollout_state, double Ts, const int* order, bool prefer_stage) {
 #define WARP_GO(T_, L_) assemble_solve_launch<T_, L_, Tune<T_>::rlev, Tune<T_>::minb>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts)
 #define BLOCK_GO(T_, L_, NT_) assemble_solve_block_launch<T_, L_, NT_>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts)
     const int ns = mp.N + 1;
@@ -264,7 +284,7 @@ int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings
     if (precision == 1) {
         if (ns <= 16) WARP_GO(double, 4); else if (ns <= 32) WARP_GO(double, 5);
         else if (ns <= 64) BLOCK_GO(double, 6, 64); else BLOCK_GO(double, 7, 128);
-    } else if (use_pair_kernels() && ns <= 64) {
+    } else if (use_pair_kernels() && ns <= 64 && !(prefer_stage && ns <= 32 && !force_pair_kernels())) {
         return launch_assemble_solve_pair(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status,
                                           flags, B, s, rollout_state, Ts, order);
     } else {

@@ -180,6 +180,14 @@ static void assemble_solve_pair_launch(const MpcParams& mp, const AdmmSettings& 
         control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, rs, Ts, order);
 }
 
+void preload_pair_kernels(int N) {
+    const int ns = N + 1;
+    cudaFuncAttributes fa;
+    if (ns <= 16) { cudaFuncGetAttributes(&fa, assemble_solve_pair_kernel<8, true, kPairMinBlocks>); cudaFuncGetAttributes(&fa, assemble_solve_pair_kernel<8, false, kPairMinBlocks>); }
+    else if (ns <= 32) { cudaFuncGetAttributes(&fa, assemble_solve_pair_kernel<16, true, kPairMinBlocks>); cudaFuncGetAttributes(&fa, assemble_solve_pair_kernel<16, false, kPairMinBlocks>); }
+    else if (ns <= 64) { cudaFuncGetAttributes(&fa, assemble_solve_pair_kernel<32, true, kPairMinBlocks>); cudaFuncGetAttributes(&fa, assemble_solve_pair_kernel<32, false, kPairMinBlocks>); }
+}
+
 int launch_solve_qp_pair(int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax, const double* l,
                          const double* u, double* x_out, int* iters, int* status, int B, cudaStream_t s) {
     const int ns = N + 1;

@@ -27,7 +27,7 @@ void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridV
                     double sm, double* ub, double* lb, double* cells_sm, int* flags, int B, bool rowspan_ok,
                     cudaStream_t st, const double* state = nullptr, int* wp_id_out = nullptr,
                     double* spatial_out = nullptr, double length = 0.0, const int* prev_iters = nullptr,
-                    int* order_out = nullptr);
+                    int* order_out = nullptr, int* long_out = nullptr);
 void launch_localize(const double* state, int* wp_id, double* spatial, int* flags, const PathView& pv, double length,
                      int B, cudaStream_t st);
 void launch_rollout(double* state, const double* spatial, const int* wp_id, const double* u, const int* flags,
@@ -42,8 +42,11 @@ int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* 
 int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings& st, const PathView& pv,
                           const double* spatial, const int* wp_id, double* control, const double* ub, const double* lb,
                           int* infeas, double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
-                          cudaStream_t s, double* rollout_state = nullptr, double Ts = 0.0, const int* order = nullptr);
+                          cudaStream_t s, double* rollout_state = nullptr, double Ts = 0.0, const int* order = nullptr,
+                          bool prefer_stage = false);
 
+void preload_solve_kernels(int precision, int N);
+void preload_pair_kernels(int N);
 // admm_pair.cu (fp32, N + 1 <= 64)
 int launch_solve_qp_pair(int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax, const double* l,
                          const double* u, double* x_out, int* iters, int* status, int B, cudaStream_t s);

@@ -405,6 +405,7 @@ struct RaycastArgs {
     // the ADMM iteration count of their previous solve, longest first (see plan_solve_order)
     const int* prev_iters;
     int* order_out;
+    int* long_out;  // host-mapped: number of live scenarios whose previous solve took >= kLongSolve iterations
 };
 
 // Solve order for the paired ADMM kernel.  Its warps hold 2-4 scenarios that run in lockstep until the slowest is
@@ -413,8 +414,10 @@ struct RaycastArgs {
 // (25 iterations per bucket = one termination check), longest first: warp-mates get similar iteration counts and
 // the long solves start first (shorter tail).  One CTA, shared-memory counting sort; the order inside a bucket is
 // arbitrary, which cannot change any result: a scenario's arithmetic never depends on its warp-mates.
+constexpr int kLongSolve = 300;
+
 __device__ void plan_solve_order(const int* __restrict__ prev_iters, const int* __restrict__ flags, int* __restrict__ order,
-                                 int B) {
+                                 int* long_out, int B) {
     constexpr int NB = 192;  // 25 iterations per bucket: covers OSQP's default max_iter = 4000
     __shared__ int hist[NB], cursor[NB];
     for (int i = threadIdx.x; i < NB; i += blockDim.x) hist[i] = 0;
@@ -427,8 +430,13 @@ __device__ void plan_solve_order(const int* __restrict__ prev_iters, const int* 
     for (int b = threadIdx.x; b < B; b += blockDim.x) atomicAdd(&hist[bucket(b)], 1);
     __syncthreads();
     if (threadIdx.x == 0) {
-        int run = 0;
-        for (int i = 0; i < NB; ++i) { cursor[i] = run; run += hist[i]; }
+        int run = 0, nlong = 0;
+        for (int i = 0; i < NB; ++i) {
+            cursor[i] = run; run += hist[i];
+            if (i < NB - 1 && (NB - 1 - i) * 25 >= kLongSolve) nlong += hist[i];
+        }
+        // feeds the host's choice between the paired and the lane-per-stage solve kernel for a LATER step (engine.cu)
+        if (long_out) *long_out = nlong;
     }
     __syncthreads();
     for (int b = threadIdx.x; b < B; b += blockDim.x) order[atomicAdd(&cursor[bucket(b)], 1)] = b;
@@ -446,7 +454,7 @@ raycast_kernel(RaycastArgs a) {
     const int N = a.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int ray_ctas = a.order_out ? (int)gridDim.x - 1 : (int)gridDim.x;
     if ((int)blockIdx.x == ray_ctas) {  // the extra CTA: plans the solve order while the others walk rays
-        plan_solve_order(a.prev_iters, a.flags, a.order_out, a.B);
+        plan_solve_order(a.prev_iters, a.flags, a.order_out, a.long_out, a.B);
         return;
     }
     // shared layout: [mbarriers: 8 x u64][staging slabs][per-warp scratch: segs, prev_cells, nsegs]
@@ -647,9 +655,9 @@ void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridV
                     const int2* rowspan, int max_rows, const uint32_t* ray_cells, const int* ray_len, const int* wp_id, int first_offset, int N, double min_width,
                     double sm, double* ub, double* lb, double* cells_sm, int* flags, int B, bool rowspan_ok,
                     cudaStream_t st, const double* state, int* wp_id_out, double* spatial_out, double length,
-                    const int* prev_iters, int* order_out) {
+                    const int* prev_iters, int* order_out, int* long_out) {
     RaycastArgs a;
-    a.prev_iters = prev_iters; a.order_out = order_out;
+    a.prev_iters = prev_iters; a.order_out = order_out; a.long_out = long_out;
     a.state = state; a.wp_id_out = wp_id_out; a.spatial_out = spatial_out; a.length = length;
     a.grids = grids; a.grid_stride_words = grid_stride_words; a.g = g; a.pv = pv; a.rowspan = rowspan; a.wp_id = wp_id;
     a.ray_cells = ray_cells; a.ray_len = ray_len;
