@@ -19,7 +19,7 @@ void launch_rasterize(const uint32_t* base, uint32_t* grids, int words, const Gr
 void launch_compute_width(const uint32_t* grid, const GridView& g, const PathView& pv, double max_width, double* ub,
                           double* lb, double* border, int* err, cudaStream_t st);
 int raycast_plan(const GridView& g, int N, bool shared_grid, int max_rows, bool rowspan_ok, int* warps, int* stage_rows,
-                 size_t* smem);
+                 size_t* smem, int B = 0);
 void launch_build_ray_table(const GridView& g, const PathView& pv, uint32_t* cells, int* len, int max_len,
                             cudaStream_t st);
 void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridView& g, const PathView& pv,

@@ -507,8 +507,9 @@ def test_solve_order_and_kernel_variant_do_not_change_the_answers(tmp_path):
         warp) must not change a single bit -- a scenario's arithmetic never depends on its warp-mates;
     (b) the paired-stage and the lane-per-stage fp32 kernels are different roundings of the same OSQP iteration:
         identical iteration counts where OSQP solves, controls within the fp32 tolerance."""
-    a = _run_variant(tmp_path, "pair_ordered")
-    b = _run_variant(tmp_path, "pair_unordered", MPC_SOLVE_ORDER="off")
+    # MPC_ADMM_KERNEL pins the solve kernel (by default the engine switches per step on the planner's long-solve count)
+    a = _run_variant(tmp_path, "pair_ordered", MPC_ADMM_KERNEL="pair")
+    b = _run_variant(tmp_path, "pair_unordered", MPC_ADMM_KERNEL="pair", MPC_SOLVE_ORDER="off")
     for k in ("state", "u", "control", "flags", "iters", "qp_status"):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
     c = _run_variant(tmp_path, "stage", MPC_ADMM_KERNEL="stage")
