@@ -73,11 +73,14 @@ template <int LPS> struct GroupComm {
     // the value the previous / next STAGE holds
     __device__ __forceinline__ f2 to_next(f2 p) const { return mk(prev(p.y), p.x); }
     __device__ __forceinline__ f2 from_next(f2 p) const { return mk(p.y, next(p.x)); }
-    __device__ __forceinline__ float max(float v) const {
-        if (LPS == 32) return __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(v)));  // v >= 0
+    __device__ __forceinline__ float max(float v) const {  // v >= 0
+        if constexpr (LPS == 32) {
+            return __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(v)));
+        } else {
 #pragma unroll
-        for (int s = LPS / 2; s > 0; s >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, s, LPS));
-        return v;
+            for (int s = LPS / 2; s > 0; s >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, s, LPS));
+            return v;
+        }
     }
     __device__ __forceinline__ float sum(float v) const {
 #pragma unroll
