@@ -185,6 +185,11 @@ int mpc_run_closed_loop(mpc_engine *h, int32_t max_steps, double *h_stats);
 /* host-buffer variant of one step (the e2e path): H2D of h_state[4][B], step, D2H of h_u_out[B][2]
  * and the new h_state.  Synchronous. */
 int mpc_step_host(mpc_engine *h, double *h_state, double *h_u_out, int32_t *h_flags);
+/* mpc_step_host copies through an internal page-locked block when the caller's buffers are pageable.  When
+ * they are page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory, or the engine's own block
+ * returned here: state[4][B] | u[B][2] | flags[B], valid until the next mpc_scenarios_init) the DMA engines
+ * address them directly and the whole step -- H2D, the two kernels, D2H -- is one CUDA-graph launch. */
+int mpc_host_io(mpc_engine *h, double **h_state, double **h_u, int32_t **h_flags);
 /* device views of the engine-owned scenario arrays (for zero-copy inspection from torch/ctypes) */
 int mpc_scenarios_ptrs(mpc_engine *h, double **d_state, double **d_spatial, int32_t **d_wp_id,
                        double **d_control, double **d_ub, double **d_lb, double **d_u, int32_t **d_iters,

@@ -40,7 +40,7 @@ EXPORTS = [
     "mpc_raycast", "mpc_update_path_constraints", "mpc_assemble_solve", "mpc_solve_qp", "mpc_rollout",
     "mpc_scenarios_init", "mpc_scenarios_set_state", "mpc_step", "mpc_run_closed_loop", "mpc_step_host",
     "mpc_scenarios_ptrs", "mpc_scenarios_read", "mpc_launch_count", "mpc_set_profiling", "mpc_get_profile",
-    "mpc_speed_profile", "mpc_predict_xy",
+    "mpc_speed_profile", "mpc_predict_xy", "mpc_host_io",
 ]
 
 _lib = None
@@ -87,6 +87,7 @@ def load():
     L.mpc_step.argtypes = [vp]
     L.mpc_run_closed_loop.argtypes = [vp, C.c_int32, c_double_p]
     L.mpc_step_host.argtypes = [vp, c_double_p, c_double_p, c_int_p]
+    L.mpc_host_io.argtypes = [vp, C.POINTER(c_double_p), C.POINTER(c_double_p), C.POINTER(c_int_p)]
     L.mpc_scenarios_ptrs.argtypes = [vp] + [C.POINTER(vp)] * 11
     L.mpc_scenarios_read.argtypes = [vp, c_double_p, c_double_p, c_double_p, c_int_p, c_int_p, c_int_p, c_int_p,
                                      c_int_p, c_double_p, c_double_p]
@@ -287,6 +288,15 @@ class Engine:
         _check(self.L.mpc_run_closed_loop(self.h, int(max_steps), _dp(stats)))
         return dict(zip(("scenario_steps", "qp_solves", "admm_iters", "qp_fallbacks", "dead", "finished",
                          "sum_abs_ey", "max_abs_ey"), stats.tolist()))
+
+    def host_io(self):
+        """The engine's page-locked I/O block as numpy views (state[4, B], u[B, 2], flags[B]); step_host on these
+        skips the staging copies and runs as a single graph launch.  Valid until the next scenarios_init."""
+        ps, pu, pf = c_double_p(), c_double_p(), c_int_p()
+        _check(self.L.mpc_host_io(self.h, C.byref(ps), C.byref(pu), C.byref(pf)))
+        B = self.B
+        return (np.ctypeslib.as_array(ps, shape=(4, B)), np.ctypeslib.as_array(pu, shape=(B, 2)),
+                np.ctypeslib.as_array(pf, shape=(B,)))
 
     def step_host(self, state4xB, u_out, flags=None):
         _check(self.L.mpc_step_host(self.h, _dp(state4xB), _dp(u_out),

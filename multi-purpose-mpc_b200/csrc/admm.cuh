@@ -126,7 +126,11 @@ __device__ __forceinline__ float tmax(float a, float b) { return fmaxf(a, b); } 
 __device__ __forceinline__ double tmax(double a, double b) { return fmax(a, b); }
 __device__ __forceinline__ float tmin(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ double tmin(double a, double b) { return fmin(a, b); }
-__device__ __forceinline__ float trsqrt(float v) { return rsqrtf(v); }  // MUFU.RSQ (2 ulp): scaling factors only
+__device__ __forceinline__ float trsqrt(float v) {  // bare MUFU.RSQ (2 ulp): scaling factors only; the argument is clamped
+    float r;                                         // to [1e-4, 1e4], so rsqrtf()'s denormal fix-up is dead weight
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
 __device__ __forceinline__ double trsqrt(double v) { return 1.0 / sqrt(v); }
 template <typename T> __device__ __forceinline__ T limit_scaling(T v) {
     v = v < T(kMinScaling) ? T(1) : v;

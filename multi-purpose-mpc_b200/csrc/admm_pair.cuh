@@ -117,7 +117,14 @@ __device__ __forceinline__ float limit_scaling_f(float v) {
     v = v < (float)kMinScaling ? 1.0f : v;
     return fminf(v, (float)kMaxScaling);
 }
-__device__ __forceinline__ f2 prsqrt_lim(f2 v) { return mk(rsqrtf(limit_scaling_f(v.x)), rsqrtf(limit_scaling_f(v.y))); }
+// MUFU.RSQ alone: rsqrtf() wraps it in a denormal range fix-up (FSETP + two predicated FMUL) that can never trigger here,
+// the argument is clamped to [1e-4, 1e4] -- bit-identical result, 3 instructions fewer per value (78 per Ruiz pass)
+__device__ __forceinline__ float rsq_normal(float v) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ f2 prsqrt_lim(f2 v) { return mk(rsq_normal(limit_scaling_f(v.x)), rsq_normal(limit_scaling_f(v.y))); }
 
 // OSQP scale_data (Ruiz equilibration of the KKT matrix + cost scaling), paired layout.
 template <int LPS>

@@ -88,6 +88,11 @@ struct mpc_engine {
     double* pin_u = nullptr;
     int* pin_flags = nullptr;
     int pin_B = 0;
+    // mpc_step_host on caller-pinned memory: H2D + the two step kernels + D2H as ONE graph launch, keyed by the pointers
+    cudaGraphExec_t io_graph[2] = {nullptr, nullptr};
+    const void* io_key[3] = {nullptr, nullptr, nullptr};
+    int io_B = 0;
+    const void* pinned_seen[3] = {nullptr, nullptr, nullptr};  // host pointers already found to be page-locked
     // profiling
     int profiling = 0;
     int no_solve_order = 0;  // MPC_SOLVE_ORDER=off: scenarios are solved in index order (A/B switch)
@@ -118,6 +123,12 @@ static void drop_graph(mpc_engine* h) {
         h->graph_exec[i] = nullptr;
     }
     h->graph_B = 0;
+    for (int i = 0; i < 2; ++i) {
+        if (h->io_graph[i]) cudaGraphExecDestroy(h->io_graph[i]);
+        h->io_graph[i] = nullptr;
+    }
+    h->io_B = 0;
+    h->pinned_seen[0] = h->pinned_seen[1] = h->pinned_seen[2] = nullptr;
 }
 
 extern "C" int mpc_set_error_(int code, const char* msg) { return fail(code, msg); }
@@ -707,29 +718,125 @@ int mpc_run_closed_loop(mpc_engine* h, int32_t max_steps, double* h_stats) {
     return 0;
 }
 
+static int ensure_pinned_io(mpc_engine* h) {
+    const int B = h->B;
+    if (h->pin_B >= B && h->pin_state) return 0;
+    const size_t io_bytes = 6 * (size_t)B * sizeof(double) + (size_t)B * sizeof(int);
+    if (h->pin_state) cudaFreeHost(h->pin_state);
+    h->pin_state = nullptr;
+    h->pin_B = 0;
+    CUDA_OK(cudaMallocHost(&h->pin_state, io_bytes));
+    h->pin_u = h->pin_state + 4 * (size_t)B;
+    h->pin_flags = reinterpret_cast<int*>(h->pin_state + 6 * (size_t)B);
+    h->pin_B = B;
+    return 0;
+}
+
+int mpc_host_io(mpc_engine* h, double** h_state, double** h_u, int32_t** h_flags) {
+    if (!h || h->B <= 0) return fail(MPC_E_STATE, "mpc_scenarios_init first");
+    if (int r = ensure_pinned_io(h)) return r;
+    if (h_state) *h_state = h->pin_state;
+    if (h_u) *h_u = h->pin_u;
+    if (h_flags) *h_flags = h->pin_flags;
+    return 0;
+}
+
+// is [p, p + bytes) page-locked host memory the DMA engines can address directly?  (remembered per pointer)
+static bool host_pinned(mpc_engine* h, int slot, const void* p, size_t bytes) {
+    if (!p) return true;
+    if (h->pinned_seen[slot] == p) return true;
+    cudaPointerAttributes a0, a1;
+    if (cudaPointerGetAttributes(&a0, p) != cudaSuccess ||
+        cudaPointerGetAttributes(&a1, static_cast<const char*>(p) + bytes - 1) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost) return false;
+    h->pinned_seen[slot] = p;
+    return true;
+}
+
+// H2D state -> localise+raycast -> assemble+solve+rollout -> D2H (state, u, flags): one graph, one launch
+static int ensure_io_graph(mpc_engine* h, double* h_state, double* h_u_out, int32_t* h_flags) {
+    if (h->io_graph[0] && h->io_graph[1] && h->io_B == h->B && h->io_key[0] == h_state && h->io_key[1] == h_u_out &&
+        h->io_key[2] == h_flags)
+        return 0;
+    for (int i = 0; i < 2; ++i) {
+        if (h->io_graph[i]) cudaGraphExecDestroy(h->io_graph[i]);
+        h->io_graph[i] = nullptr;
+    }
+    const size_t B = h->B;
+    cudaStream_t cap = h->stream, own = nullptr;
+    if (cap == nullptr) {
+        CUDA_OK(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+        cap = own;
+    }
+    cudaStream_t saved = h->stream;
+    h->stream = cap;
+    int r = 0;
+    cudaError_t e = cudaSuccess;
+    const bool one_block = h_u_out == h_state + 4 * B && (!h_flags || h_flags == reinterpret_cast<int32_t*>(h_state + 6 * B));
+    for (int v = 0; v < 2 && e == cudaSuccess && !r; ++v) {
+        cudaGraph_t graph = nullptr;
+        e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) break;
+        const int64_t l0 = h->launches;
+        cudaMemcpyAsync(h->s_state.p, h_state, 4 * B * sizeof(double), cudaMemcpyHostToDevice, cap);
+        r = enqueue_step(h, false, false, v == 1);
+        h->launches = l0;
+        if (one_block) {  // the caller's buffers are laid out like s_io (mpc_host_io): one copy
+            cudaMemcpyAsync(h_state, h->s_io.p, 6 * B * sizeof(double) + (h_flags ? B * sizeof(int) : 0), cudaMemcpyDeviceToHost, cap);
+        } else {
+            cudaMemcpyAsync(h_state, h->s_state.p, 4 * B * sizeof(double), cudaMemcpyDeviceToHost, cap);
+            cudaMemcpyAsync(h_u_out, h->s_u.p, 2 * B * sizeof(double), cudaMemcpyDeviceToHost, cap);
+            if (h_flags) cudaMemcpyAsync(h_flags, h->s_flags.p, B * sizeof(int), cudaMemcpyDeviceToHost, cap);
+        }
+        e = cudaStreamEndCapture(cap, &graph);
+        if (e == cudaSuccess && !r) e = cudaGraphInstantiate(&h->io_graph[v], graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+    }
+    h->stream = saved;
+    if (own) cudaStreamDestroy(own);
+    if (e != cudaSuccess || r) {
+        for (int i = 0; i < 2; ++i) {
+            if (h->io_graph[i]) cudaGraphExecDestroy(h->io_graph[i]);
+            h->io_graph[i] = nullptr;
+        }
+        return r ? r : fail(MPC_E_CUDA, std::string("io graph capture: ") + cudaGetErrorString(e));
+    }
+    h->io_B = h->B;
+    h->io_key[0] = h_state; h->io_key[1] = h_u_out; h->io_key[2] = h_flags;
+    return 0;
+}
+
 int mpc_step_host(mpc_engine* h, double* h_state, double* h_u_out, int32_t* h_flags) {
     if (!h || h->B <= 0) return fail(MPC_E_STATE, "mpc_scenarios_init first");
     if (int r = need(h, true, true)) return r;
     if (!h_state || !h_u_out) return fail(MPC_E_INVALID, "null host pointer");
-    const int B = h->B;
-    const size_t io_bytes = 6 * (size_t)B * sizeof(double) + (size_t)B * sizeof(int);
-    if (h->pin_B < B) {
-        if (h->pin_state) cudaFreeHost(h->pin_state);
-        CUDA_OK(cudaMallocHost(&h->pin_state, io_bytes));
-        h->pin_u = h->pin_state + 4 * (size_t)B;
-        h->pin_flags = reinterpret_cast<int*>(h->pin_state + 6 * (size_t)B);
-        h->pin_B = B;
-    }
+    const size_t B = h->B;
     cudaStream_t s = h->stream;
-    memcpy(h->pin_state, h_state, 4 * (size_t)B * sizeof(double));
-    CUDA_OK(cudaMemcpyAsync(h->s_state.p, h->pin_state, 4 * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, s));
+    // page-locked caller buffers (mpc_host_io, cudaHostAlloc / cudaHostRegister, torch pin_memory): no staging, and the
+    // whole step -- both copies included -- is one graph launch
+    if (host_pinned(h, 0, h_state, 4 * B * sizeof(double)) && host_pinned(h, 1, h_u_out, 2 * B * sizeof(double)) &&
+        host_pinned(h, 2, h_flags, B * sizeof(int))) {
+        if (int r = ensure_io_graph(h, h_state, h_u_out, h_flags)) return r;
+        CUDA_OK(cudaGraphLaunch(h->io_graph[prefer_stage_kernel(h) ? 1 : 0], s));
+        h->launches += 2;
+        CUDA_OK(cudaStreamSynchronize(s));
+        return 0;
+    }
+    // pageable caller buffers: staged through the engine's pinned block
+    if (int r = ensure_pinned_io(h)) return r;
+    const size_t io_bytes = 6 * B * sizeof(double) + B * sizeof(int);
+    memcpy(h->pin_state, h_state, 4 * B * sizeof(double));
+    CUDA_OK(cudaMemcpyAsync(h->s_state.p, h->pin_state, 4 * B * sizeof(double), cudaMemcpyHostToDevice, s));
     if (int r = enqueue_step(h, false, false, prefer_stage_kernel(h))) return r;
     // state | u | flags are one device allocation (s_io): one device-to-host copy
     CUDA_OK(cudaMemcpyAsync(h->pin_state, h->s_io.p, io_bytes, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
-    memcpy(h_state, h->pin_state, 4 * (size_t)B * sizeof(double));
-    memcpy(h_u_out, h->pin_u, 2 * (size_t)B * sizeof(double));
-    if (h_flags) memcpy(h_flags, h->pin_flags, (size_t)B * sizeof(int));
+    memcpy(h_state, h->pin_state, 4 * B * sizeof(double));
+    memcpy(h_u_out, h->pin_u, 2 * B * sizeof(double));
+    if (h_flags) memcpy(h_flags, h->pin_flags, B * sizeof(int));
     return 0;
 }
 

@@ -277,6 +277,23 @@ def test_closed_loop_graph_equals_stepwise(engine_factory):
     for _ in range(5):
         c.step_host(hs, hu)
     assert np.array_equal(hs, oa["state"]) and np.array_equal(hu, oa["u"])
+    # page-locked caller buffers (the engine's own I/O block, and torch pinned memory with separate buffers): no staging,
+    # one graph launch per step -- same bits
+    d = engine_factory(precision=1)
+    d.scenarios_init(st0)
+    ps, pu, pf = d.host_io()
+    ps[:] = st0
+    for _ in range(5):
+        d.step_host(ps, pu, pf)
+    assert np.array_equal(ps, oa["state"]) and np.array_equal(pu, oa["u"]) and np.array_equal(pf, oa["flags"])
+    import torch
+    e = engine_factory(precision=1)
+    e.scenarios_init(st0)
+    ts = torch.from_numpy(st0.copy()).pin_memory()
+    tu = torch.zeros((st0.shape[1], 2), dtype=torch.float64).pin_memory()
+    for _ in range(5):
+        e.step_host(ts.numpy(), tu.numpy())
+    assert np.array_equal(ts.numpy(), oa["state"]) and np.array_equal(tu.numpy(), oa["u"])
 
 
 def test_batch_properties_at_c2_size(engine_factory, track):
