@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmpc_b200.so")
+# MPC_B200_LIB: developer switch for A/B runs of differently-built libraries (tools/build_variants.sh); product = in-tree .so
+LIB_PATH = os.environ.get("MPC_B200_LIB") or os.path.join(_HERE, "libmpc_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int32)

@@ -14,7 +14,11 @@ namespace mpcb {
 // ------------------------------------------------------------------------------------------------
 constexpr int kPairWarpsPerBlock = 1;
 template <int LPS> constexpr size_t pair_smem_bytes() {
-    return (size_t)kPairWarpsPerBlock * 32 * kPairRows * sizeof(f2);  // (32 / LPS) groups x [kPairRows][LPS] f2
+    return (size_t)kPairWarpsPerBlock * 32 * (kPairRows * sizeof(f2) + MPC_PCR_COEF_SMEM * PcrCoef<LPS>::kF4 * sizeof(float4));
+}   // (32 / LPS) groups x [kPairRows][LPS] f2, then per warp [pcr_coef_f4][32 lanes] float4 (PCR coefficients)
+template <int LPS> __device__ __forceinline__ float4* pair_coef_ptr(unsigned char* smem_raw, int warp, int lane) {
+    return reinterpret_cast<float4*>(smem_raw + (size_t)kPairWarpsPerBlock * 32 * kPairRows * sizeof(f2)) +
+           (size_t)warp * PcrCoef<LPS>::kF4 * 32 + lane;
 }
 
 __device__ __forceinline__ void write_solution2(int N, int gl, const f2 w[5], double* xo) {
@@ -106,8 +110,9 @@ solve_qp_pair_kernel(int N, AdmmSettings st, const f2 al2, const f2 nal2, const 
     const bool tight = live && 2 * cm.gl <= N &&
                        !(s.lo[1].x < -big && s.hi[1].x > big && s.lo[2].x < -big && s.hi[2].x > big &&
                          (2 * cm.gl + 1 > N || (s.lo[1].y < -big && s.hi[1].y > big && s.lo[2].y < -big && s.hi[2].y > big)));
-    if (!__any_sync(kFull, tight)) admm_solve2<LPS, true>(cm, s, st, al2, nal2, n, sm, live, emit);
-    else admm_solve2<LPS, false>(cm, s, st, al2, nal2, n, sm, live, emit);
+    float4* cf = pair_coef_ptr<LPS>(smem_raw, warp, lane);
+    if (!__any_sync(kFull, tight)) admm_solve2<LPS, true>(cm, s, st, al2, nal2, n, sm, cf, live, emit);
+    else admm_solve2<LPS, false>(cm, s, st, al2, nal2, n, sm, cf, live, emit);
 }
 
 template <int LPS, bool LOOSE, int MINB>
@@ -148,7 +153,7 @@ assemble_solve_pair_kernel(MpcParams mp, AdmmSettings st, const f2 al2, const f2
         const RolloutArgs ro{rollout_state, spatial, pv.kappa, wp, Ts, B};
         control_epilogue2<LPS>(cm, mp, w, r, cc, infeas, u_out, iters, qp_status, flags, b, fl, ro);
     };
-    admm_solve2<LPS, LOOSE>(cm, s, st, al2, nal2, n, sm, live, emit);
+    admm_solve2<LPS, LOOSE>(cm, s, st, al2, nal2, n, sm, pair_coef_ptr<LPS>(smem_raw, warp, lane), live, emit);
 }
 
 constexpr int kPairMinBlocks = 8;

@@ -196,12 +196,40 @@ __device__ __forceinline__ void ruiz_scale2(const GroupComm<LPS>& cm, Stage2& s,
     for (int i = 0; i < 5; ++i) { s.lo[i] = pmul(s.lo[i], s.Eb[i]); s.hi[i] = pmul(s.hi[i], s.Eb[i]); }
 }
 
+// PCR coefficients of levels 0 .. NLEV-2 ((-alpha, -beta) packed, 9 float2 per level): 54 registers at LPS = 16 that ptxas
+// cannot keep next to the iterate and parks in local memory (33 LDL.64 per pass).  MPC_PCR_COEF_SMEM keeps them in shared
+// memory instead, one float4 column per lane ([k][32 lanes], conflict-free), and a pass re-reads them with LDS.128: the
+// same bytes through the LSU, less than half the instructions.
+// With the PCR coefficients out of the register file, the per-pass operands P, lo, hi fit back into registers
+// (measured at 4096 cars, step with L2 flushed: 0.1590 ms all-LDL/LDS -> 0.1580 coefficients in smem -> 0.1556 with both
+// switches on; bit-identical results).
+#ifndef MPC_PASS_P_REG
+#define MPC_PASS_P_REG 1
+#endif
+#ifndef MPC_PASS_BOUNDS_REG
+#define MPC_PASS_BOUNDS_REG 1
+#endif
+#ifndef MPC_PCR_COEF_SMEM
+#define MPC_PCR_COEF_SMEM 1
+#endif
+template <int LPS> struct PcrCoef {  // float4 per lane
+    static constexpr int kF4 = (9 * ((LPS == 32 ? 5 : (LPS == 16 ? 4 : (LPS == 8 ? 3 : 2))) - 1) + 1) / 2;
+};
+__device__ __forceinline__ float4 lds128v(const float4* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
+
 template <int LPS> struct PairFactor {
     static constexpr int NLEV = LPS == 32 ? 5 : (LPS == 16 ? 4 : (LPS == 8 ? 3 : 2));
     f2 iv, ik, nsxv0, nsxv2, nsxk0, nsxk1, nfv, nfk;  // input elimination (per stage); couplings stored negated
     float UA[6], LA[6], DAi[6];                 // in-lane cyclic-reduction level: nonzeros of U_A (0 1 2 3 4 8), of Lo_A
                                                 // (= U_B(l-1)': same six, transposed), DA^-1 (symmetric)
+#if !MPC_PCR_COEF_SMEM
     f2 nab[NLEV - 1][9];                        // PCR levels 0 .. NLEV-2: (-alpha, -beta) packed
+#endif
     float last[9];                              // PCR level NLEV-1: one partner (gl ^ LPS/2)
     float Dinv[6];                              // symmetric: 00 01 02 11 12 22
 };
@@ -221,7 +249,7 @@ __device__ __forceinline__ void sym6_to9(const float* S, float* M) {
 // PCR-factorise the chain of B stages.
 template <int LPS, bool LOOSE>
 __device__ __forceinline__ void factorize2(const GroupComm<LPS>& cm, const Stage2& s, PairFactor<LPS>& f, float sigma,
-                                           float rdf, const f2 rb[5], const f2* sm) {
+                                           float rdf, const f2 rb[5], const f2* sm, float4* cf) {
     constexpr int NLEV = PairFactor<LPS>::NLEV;
     const f2* a = s.a;
     const f2 rd = bc(rdf), sg = bc(sigma);
@@ -347,7 +375,14 @@ __device__ __forceinline__ void factorize2(const GroupComm<LPS>& cm, const Stage
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
             Lo[i] = -t1[i]; U[i] = -t2[i];
+#if MPC_PCR_COEF_SMEM
+            if (lev < NLEV - 1) {
+                const int j = 9 * lev + i;  // float2 index: float4 column j / 2 of this lane, half j & 1
+                reinterpret_cast<f2*>(cf + (j >> 1) * 32)[j & 1] = mk(-al[i], -be[i]);
+            }
+#else
             if (lev < NLEV - 1) f.nab[lev < NLEV - 1 ? lev : 0][i] = mk(-al[i], -be[i]);
+#endif
             else f.last[i] = has_up ? al[i] : be[i];
         }
     }
@@ -358,8 +393,14 @@ __device__ __forceinline__ void factorize2(const GroupComm<LPS>& cm, const Stage
 
 // x = S^-1 b for both stages of the lane
 template <int LPS>
-__device__ __forceinline__ void kkt_solve2(const GroupComm<LPS>& cm, const PairFactor<LPS>& f, const f2 b[5], f2 x[5]) {
+__device__ __forceinline__ void kkt_solve2(const GroupComm<LPS>& cm, const PairFactor<LPS>& f, const f2 b[5], f2 x[5],
+                                           const float4* cf) {
     constexpr int NLEV = PairFactor<LPS>::NLEV;
+#if MPC_PCR_COEF_SMEM
+    float4 cq[PcrCoef<LPS>::kF4 > 0 ? PcrCoef<LPS>::kF4 : 1];
+#pragma unroll
+    for (int k = 0; k < PcrCoef<LPS>::kF4; ++k) cq[k] = lds128v(cf + k * 32);
+#endif
     const f2 bv = pmul(f.iv, b[3]), bk = pmul(f.ik, b[4]);
     f2 bx0 = pfma(bk, f.nsxk0, pfma(bv, f.nsxv0, b[0]));
     f2 bx1 = pfma(bk, f.nsxk1, b[1]);
@@ -386,7 +427,16 @@ __device__ __forceinline__ void kkt_solve2(const GroupComm<LPS>& cm, const PairF
         const f2 n0 = mk(cm.up(R0.x, sft), cm.dn(R0.x, sft));
         const f2 n1 = mk(cm.up(R1.x, sft), cm.dn(R1.x, sft));
         const f2 n2 = mk(cm.up(R2.x, sft), cm.dn(R2.x, sft));
+#if MPC_PCR_COEF_SMEM
+        f2 nab[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int j = 9 * lev + i;
+            nab[i] = (j & 1) ? mk(cq[j >> 1].z, cq[j >> 1].w) : mk(cq[j >> 1].x, cq[j >> 1].y);
+        }
+#else
         const f2* nab = f.nab[lev];
+#endif
         const f2 s0 = pfma(nab[2], n2, pfma(nab[1], n1, pfma(nab[0], n0, R0)));
         const f2 s1 = pfma(nab[5], n2, pfma(nab[4], n1, pfma(nab[3], n0, R1)));
         const f2 s2 = pfma(nab[8], n2, pfma(nab[7], n1, pfma(nab[6], n0, R2)));
@@ -474,7 +524,7 @@ constexpr int kPairRows = 56;
 // a bystander until every scenario of the warp is done; `live` = false marks a group without a scenario.
 template <int LPS, bool LOOSE, typename Emit>
 __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s, const AdmmSettings& st, const f2 al2,
-                                            const f2 nal2, int nvar, f2* sm, bool live, Emit emit) {
+                                            const f2 nal2, int nvar, f2* sm, float4* cf, bool live, Emit emit) {
     typedef GroupComm<LPS> GC;
     const int gl = cm.gl;
     if (st.scaling > 0) ruiz_scale2<LPS>(cm, s, st.scaling, nvar);
@@ -504,7 +554,7 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
     const float sigma = (float)st.sigma;
     set_rho2<LPS, LOOSE>(sm, gl, rho, rdf, rb);
     PairFactor<LPS> f;
-    factorize2<LPS, LOOSE>(cm, s, f, sigma, rdf, rb, sm);
+    factorize2<LPS, LOOSE>(cm, s, f, sigma, rdf, rb, sm, cf);
     float nq_s = 0.0f, nq_u = 0.0f;
 #pragma unroll
     for (int i = 0; i < 5; ++i) { amax(nq_s, s.q[i]); amax(nq_u, pmul(s.q[i], sm[(16 + i) * LPS + gl])); }
@@ -540,11 +590,11 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
         for (int i = 0; i < 3; ++i) td[i] = pmul(rd, rdy[i]);
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            rhs[i] = pfma(ldsv(&sm[(49 + i) * LPS + gl]), x[i], u[i]);
+            rhs[i] = pfma(MPC_PASS_P_REG ? s.P[i] : ldsv(&sm[(49 + i) * LPS + gl]), x[i], u[i]);
             if (!(LOOSE && (i == 1 || i == 2))) tb[i] = pmul(rb[i], rbd[i]);
         }
         At_apply2<LPS, LOOSE>(cm, s, td, tb, rhs, rhs);  // rhs = P x + u + A'(rho r);  S D = -rhs
-        kkt_solve2<LPS>(cm, f, rhs, dl);
+        kkt_solve2<LPS>(cm, f, rhs, dl, cf);
 #pragma unroll
         for (int i = 0; i < 5; ++i) { dl[i] = pmul(dl[i], nal2); x[i] = padd(x[i], dl[i]); }  // dl = alpha D
         A_apply2<LPS, LOOSE>(cm, s, dl, s1d, s1b);
@@ -559,7 +609,8 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
             if (LOOSE && (i == 1 || i == 2)) continue;
             const f2 wv = pfma(al2, rbd[i], s1b[i]);
             vb[i] = padd(vb[i], wv);
-            const f2 zn = pmin(pmax(vb[i], ldsv(&sm[(39 + i) * LPS + gl])), ldsv(&sm[(44 + i) * LPS + gl]));
+            const f2 zn = MPC_PASS_BOUNDS_REG ? pmin(pmax(vb[i], s.lo[i]), s.hi[i])
+                                              : pmin(pmax(vb[i], ldsv(&sm[(39 + i) * LPS + gl])), ldsv(&sm[(44 + i) * LPS + gl]));
             const f2 step = psub(zn, zb[i]);
             zb[i] = zn;
             rbd[i] = psub(padd(rbd[i], s1b[i]), step);
@@ -734,7 +785,7 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
                     }
                     set_rho2<LPS, LOOSE>(sm, gl, rho, rdf, rb);
                     rd = bc(rdf);
-                    factorize2<LPS, LOOSE>(cm, s, f, sigma, rdf, rb, sm);
+                    factorize2<LPS, LOOSE>(cm, s, f, sigma, rdf, rb, sm, cf);
                 }
             }
         }

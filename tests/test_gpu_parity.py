@@ -589,3 +589,97 @@ def test_qp_non_default_osqp_settings(orc, precision, settings):
         assert err[:, ~is_kappa].max() <= (1e-4 if precision == 1 else 1e-3), err[:, ~is_kappa].max()
         if precision == 1:
             assert err.max() <= 1e-4
+
+
+def _start_states(track, sc):
+    w = sc["start_wp"]
+    return np.ascontiguousarray(np.stack([track.wp_x[w] - sc["e_y"] * np.sin(track.wp_psi[w]),
+                                          track.wp_y[w] + sc["e_y"] * np.cos(track.wp_psi[w]),
+                                          track.wp_psi[w] + sc["e_psi"], track.length_cum[w]]))
+
+
+def test_c3_full_size_obstacle_scenarios(engine_factory, track, orc, orc_path):
+    """BASELINE configs[2] at its FULL size on one GPU: 65 536 scenarios, per-scenario obstacle sets (65 536 bit grids,
+    2 GB).  The scenarios are 32 768 distinct ones followed by an exact replica of them, so the second half of every
+    output must equal the first half bit for bit (no cross-scenario interference at scale, solve order included); a
+    sample is checked against the oracle: rasters and drivable widths bit-exact, same QP status / iteration count."""
+    from mpc_b200 import distributed as D
+    half, B = 32768, 65536
+    sc = D.make_scenarios(track.n_wp, half, seed=3, kind="obstacles", wp_xy_psi=(track.wp_x, track.wp_y, track.wp_psi))
+    st = _start_states(track, sc)
+    st2 = np.ascontiguousarray(np.concatenate([st, st], axis=1))
+    obs2 = np.concatenate([sc["obs"], sc["obs"]])
+    off2 = np.concatenate([sc["obs_off"], sc["obs_off"][1:] + sc["obs_off"][-1]]).astype(np.int32)
+    eng = engine_factory(grid="free", precision=0)
+    eng.set_obstacles(obs2, off2)
+    eng.scenarios_init(st2)
+    eng.step()
+    o = eng.scenarios_read()
+    for k in ("state", "u", "iters", "qp_status", "flags", "wp_id", "ub", "lb", "control"):
+        a = o[k]
+        lo_, hi_ = (a[:, :half], a[:, half:]) if k == "state" else (a[:half], a[half:])
+        assert np.array_equal(lo_, hi_, equal_nan=True), k
+    assert np.isfinite(o["state"]).all()
+    # sample against the oracle
+    orc.set_pow_mode(False)
+    world = orc.World(orc_path, sim_cfg(orc), track.grid.shape, track.origin, track.res, 0.05)
+    rng = np.random.default_rng(0)
+    n_checked = 0
+    for b in rng.choice(half, 24, replace=False):
+        gb = eng.get_grid(int(b) + half)
+        ref = track.grid.copy()
+        for cx, cy, r in sc["obs"][sc["obs_off"][b]:sc["obs_off"][b + 1]]:
+            orc.add_obstacle(ref, track.origin, track.res, cx, cy, r)
+        assert np.array_equal(gb, ref), b
+        r = world.step(gb, st[:, b], np.zeros(60), 0)
+        if r["ret"] & 4:  # no free segment at the first waypoint (rp.py:545-547: ValueError): flagged, not solved
+            assert o["flags"][b] & (4 | 16), b
+            continue
+        assert r["wp_id"] == o["wp_id"][b]
+        assert np.array_equal(r["ub"], o["ub"][b]) and np.array_equal(r["lb"], o["lb"][b]), b
+        assert r["qp_status"] == o["qp_status"][b], (b, r["qp_status"], o["qp_status"][b])
+        if r["qp_status"] == 1:
+            assert r["iters"] == o["iters"][b]
+            assert np.abs(r["u"] - o["u"][b]).max() <= QP_TOL
+        n_checked += 1
+    assert n_checked >= 16
+
+
+def test_c4_full_size_time_optimal_n50(engine_factory, track, orc, orc_path):
+    """BASELINE configs[3] at its FULL size on one GPU: 262 144 scenarios, N = 50, build-defined time-optimal weights
+    (SURVEY H7).  Two closed-loop steps; the batch is 131 072 scenarios + their replica (halves must agree bit for
+    bit) and a sample of the first step is checked against the oracle."""
+    from mpc_b200 import distributed as D
+    N, half, B = 50, 131072, 262144
+    Q, R, QN = [0.1, 0.0, 0.0], [0.01, 0.0], [0.1, 0.0, 5.0]
+    sc = D.make_scenarios(track.n_wp, half, seed=4)
+    st = _start_states(track, sc)
+    st2 = np.ascontiguousarray(np.concatenate([st, st], axis=1))
+    eng = engine_factory(N=N, precision=0, Q=Q, R=R, QN=QN)
+    eng.scenarios_init(st2)
+    eng.step()
+    o1 = eng.scenarios_read()
+    eng.step()
+    o2 = eng.scenarios_read()
+    for o in (o1, o2):
+        for k in ("state", "u", "iters", "qp_status", "flags", "wp_id"):
+            a = o[k]
+            lo_, hi_ = (a[:, :half], a[:, half:]) if k == "state" else (a[:half], a[half:])
+            assert np.array_equal(lo_, hi_, equal_nan=True), k
+    assert np.isfinite(o2["state"]).all()
+    assert (o2["state"][3] >= o1["state"][3]).all()  # s never decreases (v >= 0)
+    kmax = np.tan(0.66) / 0.12
+    cfg = orc.mpc_cfg(N, Q, R, QN, [-np.inf] * 3, [np.inf] * 3, [0.0, -kmax], [1.0, kmax], 4.0, 0.12, 0.06 / np.sqrt(2))
+    world = orc.World(orc_path, cfg, track.grid.shape, track.origin, track.res, 0.05)
+    orc.set_pow_mode(False)
+    rng = np.random.default_rng(1)
+    n_solved = 0
+    for b in rng.choice(half, 12, replace=False):
+        r = world.step(track.grid_obs, st[:, b], np.zeros(2 * N), 0)
+        assert r["wp_id"] == o1["wp_id"][b]
+        assert r["qp_status"] == o1["qp_status"][b], (b, r["qp_status"], o1["qp_status"][b])
+        if r["qp_status"] == 1:
+            n_solved += 1
+            assert abs(r["iters"] - o1["iters"][b]) <= 25, (b, r["iters"], o1["iters"][b])  # fp32: at most one check apart
+            assert np.abs(r["u"] - o1["u"][b]).max() <= 10 * QP_TOL
+    assert n_solved >= 6
