@@ -305,6 +305,29 @@ def main():
     ray_gbs = ray_bytes * B / (kernel_ms["raycast"] * 1e-3) / 1e9 if ray_bytes else None
     eng.close()
 
+    # the same solve kernel with the machine evenly filled: 4096 cars are 2048 warps on 1184 resident warp slots
+    # (1.73 waves, the second one 73 % full); 16 copies of the batch make the tail negligible.  Supplementary --
+    # the headline roofline above stays on the BASELINE workload.
+    saturated = None
+    if world == 1 and obstacles is None and args.precision == 0:
+        rep = 16
+        e2 = mpc_b200.Engine(precision=args.precision)
+        e2.set_path(tab, lc, T["border"], True)
+        e2.set_base_grid(grid, T["origin"], float(T["resolution"]))
+        e2.scenarios_init(np.ascontiguousarray(np.tile(states, (1, rep))))
+        for _ in range(3):
+            e2.step()
+        e2.set_profiling(True)
+        e2.run_closed_loop(max(args.steps // 2, 4))
+        p2, n2 = e2.get_profile()
+        e2.set_profiling(False)
+        it2 = e2.scenarios_read()["iters"]
+        ms2 = p2["assemble_solve"] / max(n2[2], 1)
+        fl2 = float(sum(flop_model(N_HORIZON, int(i)) for i in it2))
+        saturated = {"batch": int(B * rep), "assemble_solve_ms": ms2, "achieved": fl2 / (ms2 * 1e-3) / 1e12, "unit": "TFLOP/s",
+                     "frac": fl2 / (ms2 * 1e-3) / 1e12 / fp32_peak, "qp_solves_per_sec_kernel_only": B * rep / (ms2 * 1e-3)}
+        e2.close()
+
     # ---------------- end-to-end arm: host buffers, H2D + D2H inside the timed region -------------------
     # inputs (state[4][B]) and results (state, u[B][2], flags[B]) live in page-locked HOST memory; every step is
     # H2D + localise/raycast + assemble/solve/rollout + D2H, submitted as one graph launch by mpc_step_host
@@ -384,7 +407,8 @@ def main():
                          "traffic": 4.19e6 * B / 4096 if args.precision == 0 else None,
                          "traffic_source": "dram__bytes_read+write of one launch at 4096 scenarios, ncu --set full "
                                            "(profiles/r1_assemble_solve_pair_fp32.txt), scaled by batch",
-                         "model": "SURVEY 8d: iters*(340N+264) + 400(N+1) + (iters/25)*(142N+78) per instance, actual iteration counts"},
+                         "model": "SURVEY 8d: iters*(340N+264) + 400(N+1) + (iters/25)*(142N+78) per instance, actual iteration counts",
+                         "saturated": saturated},
             "roofline_hbm": [
                 {"kernel": "rollout_kernel (K4)", "bound": "hbm", "achieved": rollout_gbs, "peak": hbm_peak, "unit": "GB/s",
                  "frac": (rollout_gbs / hbm_peak) if rollout_gbs else None, "bytes_per_instance": 100,
