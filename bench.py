@@ -64,7 +64,9 @@ def flop_model(N, iters, n_factor=1):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The timed region is tens of
+    milliseconds, far shorter than one `nvidia-smi` process start, so the samples come from NVML in-process (pynvml,
+    ~20 us per query, one every 2 ms); `nvidia-smi` is the fallback when pynvml cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -72,9 +74,40 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nv = self.handle = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:  # NVML numbers the physical GPUs; CUDA's index may be remapped by CUDA_VISIBLE_DEVICES
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(index).uuid))
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nv = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def sample(self):
+        nv = self.nv
+        if nv is None:
+            return
+        try:
+            sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+            act = lambda bit: "Active" if (r & bit) else "Not Active"
+            self.rows.append([sm, self.sm_max, pw, act(0x8), act(0x40), act(0x20), act(0x4)])
+        except Exception:
+            pass
 
     def run(self):
         while not self.stop_flag:
+            if self.nv is not None:
+                self.sample()
+                time.sleep(0.002)
+                continue
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -87,14 +120,15 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples: neither NVML nor nvidia-smi answered"]}
         sm = sorted(float(r[0]) for r in self.rows)
         reasons = []
         for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
-            if any(r[col].lower().startswith("active") for r in self.rows):
+            if any(str(r[col]).lower().startswith("active") for r in self.rows):
                 reasons.append(name)
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows),
+                "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 def cpu_oracle_world(T, grid):
@@ -153,10 +187,31 @@ def run_reference(args, rank, world):
             "note": "reference = Python + OSQP + scikit-image, not installable offline; this arm is the C port of the "
                     "same algorithm (oracle/), which is FASTER than the reference's Python (no interpreter, no scipy "
                     "assembly at ~5 ms/step)"}
+    emit_json(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: whatever libraries print there meanwhile (NCCL's version banner, torchrun
+    notes) is routed to stderr at the file-descriptor level until emit_json restores it."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
     print(json.dumps(line), flush=True)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -232,6 +287,9 @@ def main():
         ev[k][0].record()
         eng.step()
         ev[k][1].record()
+    while not ev[-1][1].query():  # the queue drains for tens of ms: sample the clocks under load from this thread too
+        sampler.sample()
+        time.sleep(0.001)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     sampler.stop_flag = True
@@ -422,7 +480,7 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
