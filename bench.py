@@ -462,7 +462,7 @@ def main():
                          "frac": achieved / (fp32_peak if args.precision == 0 else fp32_peak / 2),
                          "peak_source": fp32_src + " (MEASURED_PEAKS.json has no CUDA-core figure)",
                          "flops_per_launch": flops_per_launch,
-                         "traffic": 4.19e6 * B / 4096 if args.precision == 0 else None,
+                         "traffic": 4.02e6 * B / 4096 if args.precision == 0 else None,
                          "traffic_source": "dram__bytes_read+write of one launch at 4096 scenarios, ncu --set full "
                                            "(profiles/r1_assemble_solve_pair_fp32.txt), scaled by batch",
                          "model": "SURVEY 8d: iters*(340N+264) + 400(N+1) + (iters/25)*(142N+78) per instance, actual iteration counts",
