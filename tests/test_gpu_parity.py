@@ -643,6 +643,19 @@ def test_c3_full_size_obstacle_scenarios(engine_factory, track, orc, orc_path):
             assert np.abs(r["u"] - o["u"][b]).max() <= QP_TOL
         n_checked += 1
     assert n_checked >= 16
+    # a wider sample for the integer / width path alone (no QP solve on the CPU): 256 scenarios, 7 680 widths, bit-exact
+    smg = 0.06 / np.sqrt(2)
+    n_w = 0
+    for b in rng.choice(half, 256, replace=False):
+        if o["flags"][b] & (2 | 4 | 8 | 16 | 32):  # not ray-cast: no free segment / off the grid, or already past the finish line
+            continue
+        gb = eng.get_grid(int(b))
+        stt, ub_o, lb_o, _ = orc.update_path_constraints(gb, track.origin, track.res, orc_path, int(o["wp_id"][b]) + 1, 30,
+                                                         2 * smg, smg)
+        assert stt == 0, b
+        assert np.array_equal(ub_o, o["ub"][b]) and np.array_equal(lb_o, o["lb"][b]), b
+        n_w += 30
+    assert n_w >= 6000
 
 
 def test_c4_full_size_time_optimal_n50(engine_factory, track, orc, orc_path):
@@ -683,3 +696,28 @@ def test_c4_full_size_time_optimal_n50(engine_factory, track, orc, orc_path):
             assert abs(r["iters"] - o1["iters"][b]) <= 25, (b, r["iters"], o1["iters"][b])  # fp32: at most one check apart
             assert np.abs(r["u"] - o1["u"][b]).max() <= 10 * QP_TOL
     assert n_solved >= 6
+
+
+def test_qp_random_sample_vs_oracle():
+    """K2 on 1024 RANDOM real MPC QPs (tools/qp_random_parity.py: random waypoint, offsets, previous plans, widths from the
+    oracle's raycast on the obstacle map; 17 % of them primal infeasible) against the oracle's OSQP restatement.
+    fp64 reproduces the trace exactly; fp32 (production) reproduces the status and the iteration count of all but a
+    handful of QPs (a borderline termination check may fall one check later), and on identical traces the primal
+    solution within the per-component bar of test_qp_matches_oracle (measured on 4096 QPs: profiles/)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("qp_random_parity", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "tools", "qp_random_parity.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    r = mod.compare(1024, seed=7)
+    a = r["fp64_eps0.001"]
+    assert a["status_equal"] == 1.0 and a["iters_equal"] == 1.0 and a["infeasible"] > 0.05
+    assert max(a["same_trace_max_err_states_v"], a["same_trace_max_err_kappa"]) <= 1e-8
+    b = r["fp64_eps1e-05"]  # the north-star's parity setting: within 1e-3 of the oracle at eps 1e-5
+    assert b["status_equal"] >= 0.995 and b["iters_equal"] >= 0.995
+    assert max(b["same_trace_max_err_states_v"], b["same_trace_max_err_kappa"]) <= QP_TOL
+    c = r["fp32_eps0.001"]
+    assert c["status_equal"] >= 0.995, c
+    assert c["iters_equal_where_solved"] >= 0.995, c
+    assert c["same_trace_max_err_states_v"] <= 5e-4, c
+    assert c["same_trace_max_rel_err_kappa"] <= 2 * QP_TOL, c   # kappa relative to max(1, |kappa|); see DESIGN.md section 5
