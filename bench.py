@@ -167,11 +167,17 @@ def run_reference(args, rank, world):
     B = args.batch
     sample = B  # every timed step = one closed-loop step of the whole per-GPU batch on the host cores
     states = scenario_states(T, B, 0, sample)
+    # every host core this process may run on -- explicitly: torchrun exports OMP_NUM_THREADS=1 to its ranks, which would
+    # otherwise throttle this arm to a single thread when the driver launches it for N > 1
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except Exception:
+        ncores = os.cpu_count() or 1
     for _ in range(max(args.warmup, 0) and 1):
-        time_cpu_port(T, grid, states[:, :64], 1)
+        time_cpu_port(T, grid, states[:, :64], 1, threads=ncores)
     per_step = []
     for _ in range(args.steps):
-        v, dt, nthr, _ = time_cpu_port(T, grid, states, 1)
+        v, dt, nthr, _ = time_cpu_port(T, grid, states, 1, threads=ncores)
         per_step.append((v, dt))
     value = float(np.mean([v for v, _ in per_step]))
     ms = float(np.mean([dt for _, dt in per_step]) * 1e3)
