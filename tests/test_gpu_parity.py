@@ -721,3 +721,93 @@ def test_qp_random_sample_vs_oracle():
     assert c["iters_equal_where_solved"] >= 0.995, c
     assert c["same_trace_max_err_states_v"] <= 5e-4, c
     assert c["same_trace_max_rel_err_kappa"] <= 2 * QP_TOL, c   # kappa relative to max(1, |kappa|); see DESIGN.md section 5
+
+
+def test_synthetic_track_other_geometry(orc):
+    """Nothing in the engine is specific to sim_map: a procedurally drawn stadium track on a 330 x 437 grid (width not
+    a multiple of 32 cells), resolution 0.01 m, origin (-0.7, -1.3), 150-odd waypoints, a 0.3 m wide free corridor.
+    Path construction by the host class (the reference's algorithm), then static widths / border cells, obstacle
+    rasters, dynamic widths and full MPC steps (fp64) against the oracle on the same tables."""
+    import mpc_b200  # noqa: F401
+    from mpc_b200 import _lib
+    from mpc_b200.map import Map
+    from mpc_b200.reference_path import ReferencePath
+    H, W, res, origin = 330, 437, 0.01, (-0.7, -1.3)
+    # centre line: a stadium (two straights + two half circles) of radius 0.9 m, straights 1.6 m long
+    R, Ls = 0.9, 1.6
+    cx0, cy0 = origin[0] + W * res / 2, origin[1] + H * res / 2
+    ang = np.linspace(-np.pi / 2, np.pi / 2, 13)
+    right = np.stack([cx0 + Ls / 2 + R * np.cos(ang), cy0 + R * np.sin(ang)], 1)
+    left = np.stack([cx0 - Ls / 2 - R * np.cos(ang), cy0 - R * np.sin(ang)], 1)
+    corners = np.concatenate([[[cx0 - Ls / 2, cy0 - R]], right, left, [[cx0 - Ls / 2, cy0 - R]]])
+    # free corridor = cells within 0.15 m of the centre line polyline (dense sampling)
+    dense = np.concatenate([np.linspace(corners[i], corners[i + 1], 200, endpoint=False) for i in range(len(corners) - 1)])
+    yy, xx = np.mgrid[0:H, 0:W]
+    px, py = origin[0] + (xx + 0.5) * res, origin[1] + (yy + 0.5) * res
+    d2 = np.full((H, W), np.inf)
+    for k in range(0, len(dense), 4):
+        d2 = np.minimum(d2, (px - dense[k, 0]) ** 2 + (py - dense[k, 1]) ** 2)
+    grid = (d2 <= 0.15 ** 2).astype(np.int8)
+    assert 0.05 < grid.mean() < 0.5
+    mp = Map.from_grid(grid, list(origin), res)
+    rp = ReferencePath(mp, list(corners[:, 0]), list(corners[:, 1]), 0.04, smoothing_distance=4, max_width=0.4, circular=True)
+    n_wp = rp.n_waypoints
+    assert 100 < n_wp < 400 and n_wp != 200
+    for wp in rp.waypoints:
+        wp.v_ref = 0.8
+    rp.version += 1
+    tab, lc, border = rp.tables()
+    pt = orc.PathTables([w.x for w in rp.waypoints], [w.y for w in rp.waypoints], [w.psi for w in rp.waypoints],
+                        [w.kappa for w in rp.waypoints], [w.v_ref for w in rp.waypoints], rp.segment_lengths, border, True)
+    orc.set_pow_mode(False)
+    # static widths + border cells (K3b)
+    st, ub_o, lb_o, border_o = orc.compute_width(grid, origin, res, pt, 0.4)
+    assert st == 0
+    assert np.array_equal(border_o, border)
+    assert np.array_equal(ub_o, [w.ub for w in rp.waypoints]) and np.array_equal(lb_o, [w.lb for w in rp.waypoints])
+    # per-scenario obstacle sets, rasters, dynamic widths, full steps
+    rng = np.random.default_rng(21)
+    B = 96
+    start = rng.integers(0, n_wp - 40, B)
+    e_y, e_psi = rng.uniform(-0.04, 0.04, B), rng.uniform(-0.1, 0.1, B)
+    xs = np.array([w.x for w in rp.waypoints]); ys = np.array([w.y for w in rp.waypoints]); ps = np.array([w.psi for w in rp.waypoints])
+    st0 = np.ascontiguousarray(np.stack([xs[start] - e_y * np.sin(ps[start]), ys[start] + e_y * np.cos(ps[start]),
+                                         ps[start] + e_psi, lc[start]]))
+    obs, off = [], [0]
+    for b in range(B):
+        for _ in range(int(rng.integers(0, 4))):
+            w = int(rng.integers(0, n_wp)); o = rng.uniform(-0.12, 0.12)
+            if abs(w - start[b]) < 6:
+                continue
+            obs.append((xs[w] - o * np.sin(ps[w]), ys[w] + o * np.cos(ps[w]), rng.uniform(0.03, 0.06)))
+        off.append(len(obs))
+    obs = np.array(obs).reshape(-1, 3)
+    eng = _lib.Engine(precision=1)
+    eng.set_path(tab, lc, border, True)
+    eng.set_base_grid(grid, list(origin), res)
+    eng.set_obstacles(obs, np.array(off, np.int32))
+    eng.scenarios_init(st0)
+    eng.step()
+    o = eng.scenarios_read()
+    kmax = np.tan(0.66) / 0.12
+    cfg = orc.mpc_cfg(30, [1.0, 0.0, 0.0], [0.5, 0.0], [1.0, 0.0, 0.0], [-np.inf] * 3, [np.inf] * 3, [0.0, -kmax],
+                      [1.0, kmax], 4.0, 0.12, 0.06 / np.sqrt(2))
+    world = orc.World(pt, cfg, grid.shape, origin, res, 0.05)
+    n_ok = 0
+    for b in range(B):
+        gb = eng.get_grid(b)
+        ref = grid.copy()
+        for cx, cy, r in obs[off[b]:off[b + 1]]:
+            orc.add_obstacle(ref, origin, res, cx, cy, r)
+        assert np.array_equal(gb, ref), b
+        r = world.step(gb, st0[:, b], np.zeros(60), 0)
+        if r["ret"] & 4:
+            assert o["flags"][b] & (4 | 16), b
+            continue
+        assert r["wp_id"] == o["wp_id"][b]
+        assert np.array_equal(r["ub"], o["ub"][b]) and np.array_equal(r["lb"], o["lb"][b]), b
+        assert r["qp_status"] == o["qp_status"][b] and r["iters"] == o["iters"][b], (b, r["iters"], o["iters"][b])
+        assert np.abs(r["u"] - o["u"][b]).max() <= 1e-7 and np.abs(r["state"] - o["state"][:, b]).max() <= 1e-7
+        n_ok += 1
+    assert n_ok >= B // 2
+    eng.close()
