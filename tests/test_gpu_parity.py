@@ -811,3 +811,48 @@ def test_synthetic_track_other_geometry(orc):
         n_ok += 1
     assert n_ok >= B // 2
     eng.close()
+
+
+@pytest.mark.parametrize("precision", [1, 0])
+@pytest.mark.parametrize("variant", ["bounded_states", "other_car_and_weights"])
+def test_other_constraints_and_parameters(engine_factory, track, orc, orc_path, precision, variant):
+    """MPC(...) arguments other than simulation.py's: FINITE bounds on e_psi and t (OSQP then treats those rows like any
+    other inequality -- the solve kernels' general path instead of the `loose` one), a longer / wider car, other
+    weights (R[1] > 0, Q[1] > 0), lower v_max / ay_max / steering limit, another sampling time.  Full step vs oracle."""
+    TF = load_golden("teacher_forced.npz")
+    B, N = 24, 30
+    if variant == "bounded_states":
+        kw = dict(xmin=[-np.inf, -0.6, -0.5], xmax=[np.inf, 0.6, 40.0])
+        L, Wd, Ts, Q, R, QN, ay, umin, umax = 0.12, 0.06, 0.05, [1.0, 0.0, 0.0], [0.5, 0.0], [1.0, 0.0, 0.0], 4.0, \
+            [0.0, -np.tan(0.66) / 0.12], [1.0, np.tan(0.66) / 0.12]
+    else:
+        kw = dict(xmin=[-np.inf] * 3, xmax=[np.inf] * 3)
+        L, Wd, Ts, Q, R, QN, ay = 0.15, 0.08, 0.04, [2.0, 0.3, 0.0], [0.2, 0.05], [3.0, 0.3, 0.1], 2.5
+        umin, umax = [0.0, -np.tan(0.5) / L], [0.8, np.tan(0.5) / L]
+    eng = engine_factory(N=N, precision=precision, Q=Q, R=R, QN=QN, car_length=L, car_width=Wd, Ts=Ts, ay_max=ay,
+                         umin=umin, umax=umax, **kw)
+    st0 = np.ascontiguousarray(TF["state"][:B].T)
+    ctrl = np.ascontiguousarray(TF["control"][:B])
+    eng.scenarios_init(st0)
+    eng.scenarios_set_state(st0, ctrl, None)
+    eng.step()
+    o = eng.scenarios_read()
+    cfg = orc.mpc_cfg(N, Q, R, QN, kw["xmin"], kw["xmax"], umin, umax, ay, L, Wd / np.sqrt(2))
+    world = orc.World(orc_path, cfg, track.grid.shape, track.origin, track.res, Ts)
+    orc.set_pow_mode(False)
+    n_solved = 0
+    for b in range(B):
+        r = world.step(track.grid_obs, TF["state"][b], ctrl[b], 0)
+        if r["ret"] & 4:
+            assert o["flags"][b] & (4 | 16)
+            continue
+        assert r["wp_id"] == o["wp_id"][b]
+        assert np.array_equal(r["ub"], o["ub"][b]) and np.array_equal(r["lb"], o["lb"][b]), b
+        assert r["qp_status"] == o["qp_status"][b], (b, r["qp_status"], o["qp_status"][b])
+        if precision == 1 or r["qp_status"] == 1:
+            assert r["iters"] == o["iters"][b], (b, r["iters"], o["iters"][b])
+        tol = 1e-7 if precision == 1 else QP_TOL
+        assert np.abs(r["u"] - o["u"][b]).max() <= tol, (b, np.abs(r["u"] - o["u"][b]).max())
+        assert np.abs(r["state"] - o["state"][:, b]).max() <= tol
+        n_solved += r["qp_status"] == 1
+    assert n_solved >= B // 2
