@@ -345,7 +345,7 @@ def test_errors_are_reported_not_swallowed(track):
     eng.close()
 
 
-@pytest.mark.parametrize("N,precision", [(10, 1), (50, 1), (100, 1), (10, 0), (50, 0)])
+@pytest.mark.parametrize("N,precision", [(10, 1), (50, 1), (100, 1), (10, 0), (50, 0), (100, 0), (20, 0), (63, 0)])
 def test_other_horizons_full_step(engine_factory, track, orc, orc_path, N, precision):
     """BASELINE configs 4/5 horizons.  N + 1 <= 32 runs warp-per-scenario, longer horizons block-per-scenario
     (shared-memory exchange); both must reproduce the oracle's step: widths bit-exact, same solver trace."""
