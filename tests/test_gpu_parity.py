@@ -856,3 +856,44 @@ def test_other_constraints_and_parameters(engine_factory, track, orc, orc_path, 
         assert np.abs(r["state"] - o["state"][:, b]).max() <= tol
         n_solved += r["qp_status"] == 1
     assert n_solved >= B // 2
+
+
+def test_raycast_dense_obstacle_fuzz(engine_factory, track, orc, orc_path):
+    """K3 under heavy clutter: 512 scenarios with 20-45 small discs each scattered over the corridor, so that most
+    horizons contain waypoints with two or more candidate segments (the sequential nearest-to-previous selection with
+    quirk Q2, rp.py:549-595), rays that close several segments, and waypoints with no free segment at all.  Widths
+    bit-exact, flags identical."""
+    import torch
+    rng = np.random.default_rng(99)
+    B = 512
+    obs, off = [], [0]
+    for b in range(B):
+        for _ in range(int(rng.integers(20, 46))):
+            w = int(rng.integers(0, track.n_wp)); o = rng.uniform(-0.2, 0.2)
+            obs.append((track.wp_x[w] - o * np.sin(track.wp_psi[w]), track.wp_y[w] + o * np.cos(track.wp_psi[w]),
+                        rng.uniform(0.01, 0.035)))
+        off.append(len(obs))
+    obs = np.array(obs)
+    eng = engine_factory(grid="free")
+    eng.set_obstacles(obs, np.array(off, np.int32))
+    wid = rng.integers(0, track.n_wp, B).astype(np.int32)
+    ub = torch.zeros((B, 30), dtype=torch.float64, device=_dev())
+    lb = torch.zeros_like(ub)
+    fl = torch.zeros(B, dtype=torch.int32, device=_dev())
+    eng.raycast(_t(wid, torch.int32), ub, lb, None, fl)
+    eng.sync()
+    ub, lb, fl = ub.cpu().numpy(), lb.cpu().numpy(), fl.cpu().numpy()
+    sm = 0.06 / np.sqrt(2)
+    orc.set_pow_mode(False)
+    n_multi = n_dead = 0
+    for b in range(B):
+        g = eng.get_grid(b)
+        st, ub_o, lb_o, _ = orc.update_path_constraints(g, track.origin, track.res, orc_path, int(wid[b]) + 1, 30, 2 * sm, sm)
+        if st != 0:
+            assert fl[b] & 4, (b, st, fl[b])
+            n_dead += 1
+            continue
+        assert fl[b] == 0, (b, fl[b])
+        assert np.array_equal(ub_o, ub[b]) and np.array_equal(lb_o, lb[b]), b
+        n_multi += int((ub_o - lb_o < 0.25).any())
+    assert n_multi > B // 4  # the clutter does narrow the corridor in a good share of the horizons
