@@ -58,7 +58,8 @@ extern "C" {
 #define MPC_ST_DEAD 2          /* infeasibility_counter reached N-1: reference exit(1)           (MPC.py:218-220) */
 #define MPC_ST_NO_SEGMENT 4    /* first horizon waypoint has no free segment: reference ValueError (rp.py:547) */
 #define MPC_ST_END_OF_PATH 8   /* non-circular path exhausted: reference exit(1)                (rp.py:367-369) */
-#define MPC_ST_INDEX_ERROR 16  /* a tested cell lies outside the grid: reference IndexError      (rp.py:496) */
+#define MPC_ST_INDEX_ERROR 16  /* a tested cell lies outside the grid: reference IndexError      (rp.py:496);
+                                  also: a ray with more than 8 free segments wider than min_width (engine capacity) */
 #define MPC_ST_FINISHED 32     /* s >= path length: the reference's while loop ends   (simulation.py:134) */
 
 typedef struct mpc_engine mpc_engine;
