@@ -1,5 +1,6 @@
+"""tools/iters_hist.py -- histogram of ADMM iteration counts per closed-loop step on the bench workload (4096 cars)."""
 import sys, os, json
-sys.path.insert(0, '/root/repo'); 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, bench, mpc_b200
 from mpc_b200 import _lib
 T, grid = bench.load_track()
