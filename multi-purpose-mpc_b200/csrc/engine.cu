@@ -79,6 +79,7 @@ struct mpc_engine {
     DevBuf<double> s_state, s_spatial, s_control, s_ub, s_lb, s_u, s_acc;
     DevBuf<int> s_wp_id, s_iters, s_qp_status, s_flags, s_infeas;
     DevBuf<int> s_order;  // solve order of the closed-loop step (geometry.cu::plan_solve_order)
+    DevBuf<double> s_stats8;  // reduced statistics of mpc_run_closed_loop
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};  // [0] paired solve kernel, [1] lane-per-stage solve kernel
     int* h_long = nullptr;   // host-mapped counter written by the solve-order planner (geometry.cu)
     int* d_long = nullptr;
@@ -195,7 +196,7 @@ int mpc_engine_destroy(mpc_engine* h) {
     h->d_obs_off.release(); h->d_rowspan.release(); h->d_err.release(); h->d_ray_cells.release(); h->d_ray_len.release();
     h->s_state.release(); h->s_spatial.release(); h->s_control.release(); h->s_ub.release(); h->s_lb.release();
     h->s_u.release(); h->s_acc.release(); h->s_wp_id.release(); h->s_iters.release(); h->s_qp_status.release();
-    h->s_flags.release(); h->s_infeas.release(); h->s_order.release(); h->s_io.release();
+    h->s_flags.release(); h->s_infeas.release(); h->s_order.release(); h->s_io.release(); h->s_stats8.release();
     if (h->pin_state) cudaFreeHost(h->pin_state);  // pin_u / pin_flags point into it
     if (h->h_long) cudaFreeHost(h->h_long);
     for (int i = 0; i < 5; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -705,13 +706,11 @@ int mpc_run_closed_loop(mpc_engine* h, int32_t max_steps, double* h_stats) {
         h->launches += 3 * (int64_t)max_steps;
     }
     if (h_stats) {
-        DevBuf<double> out;
-        CUDA_OK(out.alloc(8));
-        reduce_stats_kernel<<<1, 256, 0, h->stream>>>(h->s_acc.p, h->s_flags.p, h->B, out.p);
+        CUDA_OK(h->s_stats8.alloc(8));
+        reduce_stats_kernel<<<1, 256, 0, h->stream>>>(h->s_acc.p, h->s_flags.p, h->B, h->s_stats8.p);
         ++h->launches;
-        CUDA_OK(cudaMemcpyAsync(h_stats, out.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_OK(cudaMemcpyAsync(h_stats, h->s_stats8.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CUDA_OK(cudaStreamSynchronize(h->stream));
-        out.release();
     } else {
         CUDA_OK(cudaStreamSynchronize(h->stream));
     }
