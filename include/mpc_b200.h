@@ -207,6 +207,14 @@ int mpc_scenarios_read(mpc_engine *h, double *h_state, double *h_control, double
 int mpc_speed_profile(const double *h_li, const double *h_vmax, int32_t n, double v_min, double a_min,
                       double a_max, const mpc_config *cfg, double *h_v_out, int32_t *h_iters,
                       int32_t *h_status);
+/* The same for T tracks at once, one CTA per track (scenario sets that randomise the track).
+ * h_off[T+1]: waypoint offsets of each track in the concatenated h_li / h_vmax / h_v_out arrays (h_off[0] = 0;
+ * track t has n_t = h_off[t+1] - h_off[t] variables; h_li carries n_t - 1 lengths per track, the last slot of each
+ * track is ignored).  h_iters / h_status: [T].  No limit on n_t: tracks whose working set exceeds shared memory
+ * keep it in a global workspace. */
+int mpc_speed_profile_batch(const double *h_li, const double *h_vmax, const int32_t *h_off, int32_t T,
+                            double v_min, double a_min, double a_max, const mpc_config *cfg,
+                            double *h_v_out, int32_t *h_iters, int32_t *h_status);
 
 /* number of kernel launches enqueued by this engine since creation (bench.py's gpu_launches) */
 int64_t mpc_launch_count(mpc_engine *h);

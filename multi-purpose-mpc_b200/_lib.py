@@ -41,7 +41,7 @@ EXPORTS = [
     "mpc_raycast", "mpc_update_path_constraints", "mpc_assemble_solve", "mpc_solve_qp", "mpc_rollout",
     "mpc_scenarios_init", "mpc_scenarios_set_state", "mpc_step", "mpc_run_closed_loop", "mpc_step_host",
     "mpc_scenarios_ptrs", "mpc_scenarios_read", "mpc_launch_count", "mpc_set_profiling", "mpc_get_profile",
-    "mpc_speed_profile", "mpc_predict_xy", "mpc_host_io",
+    "mpc_speed_profile", "mpc_speed_profile_batch", "mpc_predict_xy", "mpc_host_io",
 ]
 
 _lib = None
@@ -98,6 +98,8 @@ def load():
     L.mpc_get_profile.argtypes = [vp, c_double_p, c_i64_p]
     L.mpc_speed_profile.argtypes = [c_double_p, c_double_p, C.c_int32, C.c_double, C.c_double, C.c_double,
                                     C.POINTER(MpcConfig), c_double_p, c_int_p, c_int_p]
+    L.mpc_speed_profile_batch.argtypes = [c_double_p, c_double_p, c_int_p, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                          C.POINTER(MpcConfig), c_double_p, c_int_p, c_int_p]
     for name in EXPORTS:
         f = getattr(L, name)
         if name not in ("mpc_config_default", "mpc_last_error", "mpc_launch_count"):
@@ -126,6 +128,10 @@ def default_config(**kw):
 
 def _dp(a):
     return a.ctypes.data_as(c_double_p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_int_p)
 
 
 def _ptr(t):

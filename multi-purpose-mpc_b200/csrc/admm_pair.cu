@@ -127,7 +127,8 @@ assemble_solve_pair_kernel(MpcParams mp, AdmmSettings st, const f2 al2, const f2
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = (blockIdx.x * kPairWarpsPerBlock + warp) * G + lane / LPS;
     // `order` (closed-loop path): scenarios sorted by the length of their previous solve, see geometry.cu::plan_solve_order
-    const int b = slot < B ? (order ? order[slot] : slot) : B;
+    int b = slot < B ? (order ? order[slot] : slot) : B;
+    if ((unsigned)b >= (unsigned)B) b = B;  // an `order` entry outside 0..B-1 can only be a stale / corrupt plan: idle group
     const int fl = (b < B && flags) ? flags[b] : 0;
     const bool live = b < B && !(fl & (MPC_ST_DEAD | MPC_ST_FINISHED));
     if (!__any_sync(kFull, live)) return;

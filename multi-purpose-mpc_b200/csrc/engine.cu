@@ -64,6 +64,8 @@ struct mpc_engine {
     int words = 0;
     DevBuf<uint32_t> d_base, d_grids;
     DevBuf<int> d_obs_px, d_obs_off;
+    std::vector<double> h_obs;     // per-scenario obstacle lists as given (world cx, cy, radius), kept so that a new
+    std::vector<int> h_obs_off;    // base grid can be re-rasterised (apply_obstacles)
     int grids_B = 0;  // 0: shared base grid
     bool have_grid = false;
     DevBuf<int2> d_rowspan;
@@ -79,6 +81,7 @@ struct mpc_engine {
     DevBuf<double> s_state, s_spatial, s_control, s_ub, s_lb, s_u, s_acc;
     DevBuf<int> s_wp_id, s_iters, s_qp_status, s_flags, s_infeas;
     DevBuf<int> s_order;  // solve order of the closed-loop step (geometry.cu::plan_solve_order)
+    DevBuf<unsigned char> s_bucket;  // its per-scenario scratch
     DevBuf<double> s_stats8;  // reduced statistics of mpc_run_closed_loop
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};  // [0] paired solve kernel, [1] lane-per-stage solve kernel
     int* h_long = nullptr;   // host-mapped counter written by the solve-order planner (geometry.cu)
@@ -183,7 +186,11 @@ int mpc_engine_create(const mpc_config* cfg, mpc_engine** out) {
         h->no_solve_order = (e2 && e2[0] == 'o' && e2[1] == 'f') ? 1 : 0;
     }
     cudaMemset(h->d_err.p, 0, sizeof(int));
-    for (int i = 0; i < 5; ++i) cudaEventCreate(&h->ev[i]);
+    for (int i = 0; i < 5; ++i)
+        if (cudaEventCreate(&h->ev[i]) != cudaSuccess) {
+            mpc_engine_destroy(h);
+            return fail(MPC_E_CUDA, "cudaEventCreate failed");
+        }
     *out = h;
     return 0;
 }
@@ -196,7 +203,7 @@ int mpc_engine_destroy(mpc_engine* h) {
     h->d_obs_off.release(); h->d_rowspan.release(); h->d_err.release(); h->d_ray_cells.release(); h->d_ray_len.release();
     h->s_state.release(); h->s_spatial.release(); h->s_control.release(); h->s_ub.release(); h->s_lb.release();
     h->s_u.release(); h->s_acc.release(); h->s_wp_id.release(); h->s_iters.release(); h->s_qp_status.release();
-    h->s_flags.release(); h->s_infeas.release(); h->s_order.release(); h->s_io.release(); h->s_stats8.release();
+    h->s_flags.release(); h->s_infeas.release(); h->s_order.release(); h->s_bucket.release(); h->s_io.release(); h->s_stats8.release();
     if (h->pin_state) cudaFreeHost(h->pin_state);  // pin_u / pin_flags point into it
     if (h->h_long) cudaFreeHost(h->h_long);
     for (int i = 0; i < 5; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -327,6 +334,8 @@ int mpc_set_vref(mpc_engine* h, const double* h_vref, int32_t n_wp) {
     return 0;
 }
 
+static int apply_obstacles(mpc_engine* h);
+
 int mpc_set_base_grid(mpc_engine* h, const int8_t* data, int32_t H, int32_t W, double ox, double oy, double res) {
     if (!h || !data || H <= 0 || W <= 0 || !(res > 0)) return fail(MPC_E_INVALID, "bad grid arguments");
     if (H > 32767 || W > 32767) return fail(MPC_E_UNSUPPORTED, "grid dimensions above 32767 are not supported");
@@ -344,18 +353,20 @@ int mpc_set_base_grid(mpc_engine* h, const int8_t* data, int32_t H, int32_t W, d
     h->have_grid = true;
     h->grids_B = 0;
     drop_graph(h);
-    return compute_rowspan(h);
+    if (int r = compute_rowspan(h)) return r;
+    return apply_obstacles(h);  // per-scenario obstacle sets survive a change of the base map
 }
 
-int mpc_set_obstacles(mpc_engine* h, const double* h_obs, const int32_t* h_off, int32_t B) {
-    if (!h) return fail(MPC_E_INVALID, "null engine");
-    if (!h->have_grid) return fail(MPC_E_STATE, "mpc_set_base_grid first");
-    drop_graph(h);
-    if (B <= 0 || !h_obs || !h_off) { h->grids_B = 0; return 0; }
-    const int n_obs = h_off[B];
+// Map.add_obstacles per scenario (map.py:116-137): rasterise the remembered obstacle lists onto copies of the CURRENT base
+// grid.  Called by mpc_set_obstacles and again by mpc_set_base_grid, so that a base-map change (Map.add_obstacles /
+// add_boundary on the shared map, a new Map) never silently drops the per-scenario obstacles.
+static int apply_obstacles(mpc_engine* h) {
+    const int B = (int)h->h_obs_off.size() - 1;
+    if (B <= 0) { h->grids_B = 0; return 0; }
+    const int n_obs = h->h_obs_off[B];
     std::vector<int> px(3 * (size_t)std::max(n_obs, 1));
     for (int o = 0; o < n_obs; ++o) {
-        const double cx = h_obs[3 * o], cy = h_obs[3 * o + 1], r = h_obs[3 * o + 2];
+        const double cx = h->h_obs[3 * o], cy = h->h_obs[3 * o + 1], r = h->h_obs[3 * o + 2];
         px[3 * o] = (int)std::floor((cx - h->g.ox) / h->g.res);      // map.py:131 via w2m
         px[3 * o + 1] = (int)std::floor((cy - h->g.oy) / h->g.res);
         px[3 * o + 2] = (int)std::ceil(r / h->g.res);                // map.py:129
@@ -363,7 +374,7 @@ int mpc_set_obstacles(mpc_engine* h, const double* h_obs, const int32_t* h_off, 
     CUDA_OK(h->d_obs_px.alloc(px.size()));
     CUDA_OK(h->d_obs_off.alloc(B + 1));
     CUDA_OK(cudaMemcpyAsync(h->d_obs_px.p, px.data(), px.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CUDA_OK(cudaMemcpyAsync(h->d_obs_off.p, h_off, (B + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->d_obs_off.p, h->h_obs_off.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CUDA_OK(h->d_grids.alloc((size_t)B * h->words));
     launch_rasterize(h->d_base.p, h->d_grids.p, h->words, h->g, h->d_obs_px.p, h->d_obs_off.p, B, h->stream);
     ++h->launches;
@@ -371,6 +382,19 @@ int mpc_set_obstacles(mpc_engine* h, const double* h_obs, const int32_t* h_off, 
     CUDA_OK(cudaStreamSynchronize(h->stream));
     h->grids_B = B;
     return 0;
+}
+
+int mpc_set_obstacles(mpc_engine* h, const double* h_obs, const int32_t* h_off, int32_t B) {
+    if (!h) return fail(MPC_E_INVALID, "null engine");
+    if (!h->have_grid) return fail(MPC_E_STATE, "mpc_set_base_grid first");
+    drop_graph(h);
+    if (B <= 0 || !h_obs || !h_off) { h->h_obs.clear(); h->h_obs_off.clear(); h->grids_B = 0; return 0; }
+    if (h_off[0] != 0) return fail(MPC_E_INVALID, "obstacle offsets must start at 0");
+    for (int b = 0; b < B; ++b)
+        if (h_off[b + 1] < h_off[b]) return fail(MPC_E_INVALID, "obstacle offsets must be non-decreasing");
+    h->h_obs.assign(h_obs, h_obs + 3 * (size_t)h_off[B]);
+    h->h_obs_off.assign(h_off, h_off + B + 1);
+    return apply_obstacles(h);
 }
 
 int mpc_get_grid(mpc_engine* h, int32_t b, int8_t* out) {
@@ -532,6 +556,7 @@ int mpc_scenarios_init(mpc_engine* h, const double* h_state, int32_t B) {
     CUDA_OK(h->s_qp_status.alloc(B));
     CUDA_OK(h->s_infeas.alloc(B));
     CUDA_OK(h->s_order.alloc(B));
+    CUDA_OK(h->s_bucket.alloc(B));
     h->B = B;
     drop_graph(h);
     preload_solve_kernels(h->cfg.precision, N);
@@ -586,7 +611,7 @@ static int enqueue_step(mpc_engine* h, bool with_stats, bool timed, bool stage_h
         int* order = (h->cfg.precision == 0 && B <= (1 << 16) && !h->no_solve_order) ? h->s_order.p : nullptr;
         launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->d_ray_cells.p, h->d_ray_len.p, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm,
                        h->s_ub.p, h->s_lb.p, nullptr, h->s_flags.p, B, h->rowspan_valid, s, h->s_state.p, h->s_wp_id.p,
-                       h->s_spatial.p, h->length, h->s_iters.p, order, order ? h->d_long : nullptr);
+                       h->s_spatial.p, h->length, h->s_iters.p, order, order ? h->d_long : nullptr, h->s_bucket.p);
         int r = launch_assemble_solve(h->cfg.precision, h->mp, h->st, h->pv, h->s_spatial.p, h->s_wp_id.p, h->s_control.p,
                                       h->s_ub.p, h->s_lb.p, h->s_infeas.p, h->s_u.p, nullptr, h->s_iters.p,
                                       h->s_qp_status.p, h->s_flags.p, B, s, h->s_state.p, h->cfg.Ts, order, stage_hint);

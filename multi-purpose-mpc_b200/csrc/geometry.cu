@@ -407,6 +407,7 @@ struct RaycastArgs {
     const int* prev_iters;
     int* order_out;
     int* long_out;  // host-mapped: number of live scenarios whose previous solve took >= kLongSolve iterations
+    unsigned char* bucket_of;  // [B] scratch of the planner CTA (see plan_solve_order)
 };
 
 // Solve order for the paired ADMM kernel.  Its warps hold 2-4 scenarios that run in lockstep until the slowest is
@@ -418,17 +419,25 @@ struct RaycastArgs {
 constexpr int kLongSolve = 300;
 
 __device__ void plan_solve_order(const int* __restrict__ prev_iters, const int* __restrict__ flags, int* __restrict__ order,
-                                 int* long_out, int B) {
+                                 int* long_out, unsigned char* __restrict__ bucket_of, int B) {
     constexpr int NB = 192;  // 25 iterations per bucket: covers OSQP's default max_iter = 4000
     __shared__ int hist[NB], cursor[NB];
     for (int i = threadIdx.x; i < NB; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    auto bucket = [&](int b) {
-        if (flags && (flags[b] & (MPC_ST_DEAD | MPC_ST_FINISHED))) return NB - 1;  // skipped by the solve: last
-        const int k = prev_iters[b] / 25;
-        return NB - 1 - (k < NB - 1 ? k : NB - 1);
-    };
-    for (int b = threadIdx.x; b < B; b += blockDim.x) atomicAdd(&hist[bucket(b)], 1);
+    // The ray CTAs of the same launch set MPC_ST_FINISHED / MPC_ST_DEAD in `flags` while this CTA runs, so a scenario's
+    // bucket is decided ONCE (histogram pass) and remembered in bucket_of[]; the scatter pass re-reads the remembered
+    // value, never the flags, so histogram and cursors always describe the same assignment and `order` is a permutation
+    // of 0..B-1.  A scenario that finishes during this launch merely keeps an early slot; the solve kernel re-reads its
+    // flags and skips it.
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        int k = NB - 1;  // skipped by the solve: last
+        if (!(flags && (flags[b] & (MPC_ST_DEAD | MPC_ST_FINISHED)))) {
+            const int q = prev_iters[b] / 25;
+            k = NB - 1 - (q < 0 ? 0 : (q < NB - 1 ? q : NB - 1));
+        }
+        bucket_of[b] = (unsigned char)k;
+        atomicAdd(&hist[k], 1);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0, nlong = 0;
@@ -440,7 +449,10 @@ __device__ void plan_solve_order(const int* __restrict__ prev_iters, const int* 
         if (long_out) *long_out = nlong;
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < B; b += blockDim.x) order[atomicAdd(&cursor[bucket(b)], 1)] = b;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const int slot = atomicAdd(&cursor[bucket_of[b]], 1);
+        if (slot < B) order[slot] = b;  // always true for a consistent histogram; never write past the array
+    }
 }
 
 // MODE 0: no staging (global / L1 reads).  MODE 1: one grid shared by all scenarios, staged once per CTA
@@ -455,7 +467,7 @@ raycast_kernel(RaycastArgs a) {
     const int N = a.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int ray_ctas = a.order_out ? (int)gridDim.x - 1 : (int)gridDim.x;
     if ((int)blockIdx.x == ray_ctas) {  // the extra CTA: plans the solve order while the others walk rays
-        plan_solve_order(a.prev_iters, a.flags, a.order_out, a.long_out, a.B);
+        plan_solve_order(a.prev_iters, a.flags, a.order_out, a.long_out, a.bucket_of, a.B);
         return;
     }
     // shared layout: [mbarriers: 8 x u64][staging slabs][per-warp scratch: segs, prev_cells, nsegs]
@@ -671,9 +683,9 @@ void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridV
                     const int2* rowspan, int max_rows, const uint32_t* ray_cells, const int* ray_len, const int* wp_id, int first_offset, int N, double min_width,
                     double sm, double* ub, double* lb, double* cells_sm, int* flags, int B, bool rowspan_ok,
                     cudaStream_t st, const double* state, int* wp_id_out, double* spatial_out, double length,
-                    const int* prev_iters, int* order_out, int* long_out) {
+                    const int* prev_iters, int* order_out, int* long_out, unsigned char* bucket_of) {
     RaycastArgs a;
-    a.prev_iters = prev_iters; a.order_out = order_out; a.long_out = long_out;
+    a.prev_iters = prev_iters; a.order_out = (order_out && bucket_of) ? order_out : nullptr; a.long_out = long_out; a.bucket_of = bucket_of;
     a.state = state; a.wp_id_out = wp_id_out; a.spatial_out = spatial_out; a.length = length;
     a.grids = grids; a.grid_stride_words = grid_stride_words; a.g = g; a.pv = pv; a.rowspan = rowspan; a.wp_id = wp_id;
     a.ray_cells = ray_cells; a.ray_len = ray_len;
@@ -686,7 +698,7 @@ void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridV
     const int ctas_needed = (B + warps - 1) / warps;
     // persistent-style grid: enough CTAs to fill the machine a few times over, each looping over scenarios
     const int max_ctas = 148 * 8;
-    const int grid = (ctas_needed < max_ctas ? ctas_needed : max_ctas) + (order_out ? 1 : 0);
+    const int grid = (ctas_needed < max_ctas ? ctas_needed : max_ctas) + (a.order_out ? 1 : 0);
     if (mode == 1) {
         cudaFuncSetAttribute(raycast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         raycast_kernel<1><<<grid, warps * 32, smem, st>>>(a);

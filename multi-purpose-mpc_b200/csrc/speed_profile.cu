@@ -52,11 +52,24 @@ __device__ __forceinline__ double lim_scal(double v) {
     return v > kMaxScaling ? kMaxScaling : v;
 }
 
-__global__ void speed_profile_kernel(int n, const double* __restrict__ li, const double* __restrict__ vmax, double v_min,
-                                     double a_min, double a_max, AdmmSettings st, double* __restrict__ v_out,
-                                     int* __restrict__ info /*iters, status*/) {
-    extern __shared__ double sm[];
-    const int tid = threadIdx.x, nt = blockDim.x, na = n - 1;
+// One CTA per track (blockIdx.x): the batched form serves scenario sets that randomise the track itself
+// (SURVEY 8f-1).  off[t] .. off[t+1] are track t's waypoints in the concatenated li / vmax / v_out arrays (li holds
+// n - 1 segment lengths per track, its last slot is unused).  The 27 n working doubles live in shared memory when they
+// fit and otherwise in this CTA's slice of the global workspace `ws` (L2-resident: a long track just runs slower; the
+// reference's compute_speed_profile has no size limit, rp.py:289-354).
+__global__ void speed_profile_kernel(const int* __restrict__ off, const double* __restrict__ li_all,
+                                     const double* __restrict__ vmax_all, double v_min, double a_min, double a_max,
+                                     AdmmSettings st, double* __restrict__ v_out_all, int* __restrict__ info_all /*[T][2]*/,
+                                     double* __restrict__ ws, size_t ws_stride) {
+    extern __shared__ double sm_dyn[];
+    __shared__ double tmp_red[256];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int n = off[blockIdx.x + 1] - off[blockIdx.x], na = n - 1;
+    const double* li = li_all + off[blockIdx.x];
+    const double* vmax = vmax_all + off[blockIdx.x];
+    double* v_out = v_out_all + off[blockIdx.x];
+    int* info = info_all + 2 * blockIdx.x;
+    double* sm = ws ? ws + (size_t)blockIdx.x * ws_stride : sm_dyn;
     SpShared S;
     double* p = sm;
     auto take = [&](int k) { double* r = p; p += k; return r; };
@@ -66,7 +79,7 @@ __global__ void speed_profile_kernel(int n, const double* __restrict__ li, const
     S.x = take(n); S.za = take(n); S.zb = take(n); S.ya = take(n); S.yb = take(n); S.xt = take(n); S.rhs = take(n);
     S.dx = take(n); S.dya = take(n); S.dyb = take(n);
     S.dg = take(n); S.od = take(n); S.ld = take(n); S.ra = take(n); S.rb = take(n);
-    S.tmp = take(nt);
+    S.tmp = tmp_red;
     S.ta = reinterpret_cast<int*>(take((n + 1) / 2 + 1));
     S.tb = reinterpret_cast<int*>(take((n + 1) / 2 + 1));
     // ---- problem data (rp.py:300-344) ----
@@ -246,11 +259,21 @@ __global__ void speed_profile_kernel(int n, const double* __restrict__ li, const
 
 using namespace mpcb;
 
-extern "C" int mpc_speed_profile(const double* h_li, const double* h_vmax, int32_t n, double v_min, double a_min,
-                                 double a_max, const mpc_config* cfg, double* h_v_out, int32_t* h_iters,
-                                 int32_t* h_status) {
+static size_t sp_work_doubles(int n) { return (size_t)27 * n + 2 * ((size_t)(n + 1) / 2 + 1); }
+
+extern "C" int mpc_speed_profile_batch(const double* h_li, const double* h_vmax, const int32_t* h_off, int32_t T,
+                                       double v_min, double a_min, double a_max, const mpc_config* cfg, double* h_v_out,
+                                       int32_t* h_iters, int32_t* h_status) {
     extern int mpc_set_error_(int code, const char* msg);
-    if (!h_li || !h_vmax || !h_v_out || n < 2 || n > 1000) return mpc_set_error_(MPC_E_INVALID, "bad speed-profile arguments");
+    if (!h_li || !h_vmax || !h_off || !h_v_out || T < 1) return mpc_set_error_(MPC_E_INVALID, "bad speed-profile arguments");
+    int n_max = 0;
+    for (int t = 0; t < T; ++t) {
+        const int n = h_off[t + 1] - h_off[t];
+        if (n < 2) return mpc_set_error_(MPC_E_INVALID, "a speed profile needs at least 2 waypoints (rp.py:296-297)");
+        n_max = n > n_max ? n : n_max;
+    }
+    if (h_off[0] != 0) return mpc_set_error_(MPC_E_INVALID, "track offsets must start at 0");
+    const int total = h_off[T];
     mpc_config c;
     if (cfg) c = *cfg; else mpc_config_default(&c);
     AdmmSettings st;
@@ -258,27 +281,47 @@ extern "C" int mpc_speed_profile(const double* h_li, const double* h_vmax, int32
     st.eps_prim_inf = c.eps_prim_inf; st.eps_dual_inf = c.eps_dual_inf; st.adaptive_rho_tolerance = c.adaptive_rho_tolerance;
     st.max_iter = c.max_iter; st.scaling = c.scaling; st.check_termination = c.check_termination;
     st.adaptive_rho_interval = c.adaptive_rho_interval;
-    double *d_li = nullptr, *d_vmax = nullptr, *d_v = nullptr;
-    int* d_info = nullptr;
+    double *d_li = nullptr, *d_vmax = nullptr, *d_v = nullptr, *d_ws = nullptr;
+    int *d_info = nullptr, *d_off = nullptr;
     const int nt = 256;
-    const size_t smem = ((size_t)27 * n + nt + 2 * ((n + 1) / 2 + 1)) * sizeof(double);
-    cudaError_t e = cudaMalloc(&d_li, n * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&d_vmax, n * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&d_v, n * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&d_info, 2 * sizeof(int));
-    if (e == cudaSuccess) e = cudaMemcpy(d_li, h_li, (n - 1) * sizeof(double), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_vmax, h_vmax, n * sizeof(double), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(speed_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int info[2] = {0, 0};
+    const size_t work = sp_work_doubles(n_max);
+    size_t smem = work * sizeof(double);
+    const bool spill = smem > 200 * 1024;  // longer tracks keep their vectors in a global workspace (one slice per CTA)
+    if (spill) smem = 0;
+    cudaError_t e = cudaMalloc(&d_li, (size_t)total * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_vmax, (size_t)total * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_v, (size_t)total * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_info, 2 * (size_t)T * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&d_off, ((size_t)T + 1) * sizeof(int));
+    if (e == cudaSuccess && spill) e = cudaMalloc(&d_ws, work * (size_t)T * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(d_li, h_li, (size_t)total * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_vmax, h_vmax, (size_t)total * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_off, h_off, ((size_t)T + 1) * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && smem) e = cudaFuncSetAttribute(speed_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    std::vector<int> info(2 * (size_t)T, 0);
     if (e == cudaSuccess) {
-        speed_profile_kernel<<<1, nt, smem>>>(n, d_li, d_vmax, v_min, a_min, a_max, st, d_v, d_info);
+        speed_profile_kernel<<<T, nt, smem>>>(d_off, d_li, d_vmax, v_min, a_min, a_max, st, d_v, d_info, d_ws, work);
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpy(h_v_out, d_v, n * sizeof(double), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(info, d_info, sizeof(info), cudaMemcpyDeviceToHost);
-    cudaFree(d_li); cudaFree(d_vmax); cudaFree(d_v); cudaFree(d_info);
+    if (e == cudaSuccess) e = cudaMemcpy(h_v_out, d_v, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(info.data(), d_info, info.size() * sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d_li); cudaFree(d_vmax); cudaFree(d_v); cudaFree(d_info); cudaFree(d_off); cudaFree(d_ws);
     if (e != cudaSuccess) return mpc_set_error_(MPC_E_CUDA, cudaGetErrorString(e));
-    if (h_iters) *h_iters = info[0];
-    if (h_status) *h_status = info[1];
+    for (int t = 0; t < T; ++t) {
+        if (h_iters) h_iters[t] = info[2 * t];
+        if (h_status) h_status[t] = info[2 * t + 1];
+    }
     return 0;
+}
+
+extern "C" int mpc_speed_profile(const double* h_li, const double* h_vmax, int32_t n, double v_min, double a_min,
+                                 double a_max, const mpc_config* cfg, double* h_v_out, int32_t* h_iters,
+                                 int32_t* h_status) {
+    extern int mpc_set_error_(int code, const char* msg);
+    if (n < 2) return mpc_set_error_(MPC_E_INVALID, "a speed profile needs at least 2 waypoints (rp.py:296-297)");
+    const int32_t off[2] = {0, n};
+    // the single-track ABI passes n - 1 segment lengths: pad to n so that both arrays share the offsets
+    std::vector<double> li(h_li, h_li + (n - 1));
+    li.push_back(0.0);
+    return mpc_speed_profile_batch(li.data(), h_vmax, off, 1, v_min, a_min, a_max, cfg, h_v_out, h_iters, h_status);
 }
