@@ -120,6 +120,44 @@ def fixed_pattern(N):
     return np.cumsum(Ap).astype(np.int32), np.array(rows, np.int32)
 
 
+def h1_null_direction(N, Pd, Ax):
+    """with R[1] = 0 and QN[1] = 0 (the reference's weights) the QP of MPC._init_problem is not strictly
+    convex -- (u_{N-1}.kappa : 1, x_N.e_psi : B[1,1]) costs nothing and violates no equality, so the minimiser is a
+    segment and a solver's position on it depends on scaling, rho schedule and start point.  Returns the unit vector of that
+    direction in the reference's x ordering for a batch of QPs ([B, 5N+3]; a zero row where the direction does not exist,
+    e.g. R[1] > 0), read off the constraint values: the e_psi_N dynamics row is  a.x_{N-1} + b.kappa_{N-1} - e_psi_N = ...
+    The direction is verified to lie in the null space of [diag(P); A_eq] before it is returned."""
+    Ap, Ai = fixed_pattern(N)
+    n, neq = 5 * N + 3, 3 * (N + 1)
+    Pd = np.atleast_2d(Pd); Ax = np.atleast_2d(Ax)
+    ik, ie = n - 1, 3 * N + 1                       # u_{N-1}.kappa, x_N.e_psi
+    def entry(row, col):
+        k = [j for j in range(Ap[col], Ap[col + 1]) if Ai[j] == row]
+        assert len(k) == 1
+        return Ax[:, k[0]]
+    b = entry(ie, ik)                               # coefficient of kappa_{N-1} in the e_psi_N dynamics row
+    c = entry(ie, ie)                               # -1: coefficient of e_psi_N in its own row
+    d = np.zeros((Pd.shape[0], n))
+    d[:, ik] = 1.0
+    d[:, ie] = -b / c
+    # any other equality row touching the two variables, or a cost on either, removes the direction
+    free = (Pd[:, ik] == 0) & (Pd[:, ie] == 0)
+    for col in (ik, ie):
+        for j in range(Ap[col], Ap[col + 1]):
+            if Ai[j] < neq and Ai[j] != ie:
+                free &= Ax[:, j] == 0
+    d[~free] = 0.0
+    nrm = np.linalg.norm(d, axis=1, keepdims=True)
+    return np.divide(d, nrm, out=np.zeros_like(d), where=nrm > 0)
+
+
+def h1_split(N, Pd, Ax, err):
+    """(remainder, null coordinate): err with the H1 direction projected out, and its component along it."""
+    d = h1_null_direction(N, Pd, Ax)
+    c = np.einsum("bi,bi->b", np.nan_to_num(err), d)
+    return err - c[:, None] * d, c
+
+
 def sim_cfg(orc, N=30):
     """orc_mpc_cfg of src/simulation.py:100-111"""
     kmax = np.tan(0.66) / 0.12

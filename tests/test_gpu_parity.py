@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import fixed_pattern, load_golden, sim_cfg, ulps
+from conftest import fixed_pattern, h1_split, load_golden, sim_cfg, ulps
 
 pytestmark = pytest.mark.gpu
 QP_TOL = 1e-3  # north_star: per-instance max-norm
@@ -52,19 +52,21 @@ def test_qp_matches_oracle(orc, precision, eps):
     ok = ~np.isin(sto, (-3, -4, -7))                    # OSQP returns an iterate (also for max-iter, -2)
     assert ok.sum() >= 60 and (~ok).sum() >= 6          # the fixture contains infeasible QPs too
     assert np.isnan(x[~ok]).all() and np.isnan(xo[~ok]).all()   # no solution there (MPC.py:208 path)
+    # the zero-cost direction (u_{N-1}.kappa, x_N.e_psi) is projected out of x - x_oracle, the remainder
+    # is judged in ABSOLUTE max-norm against the north-star bar, the null coordinate is reported separately.
+    rem, null = h1_split(30, Pd[ok], Ax[ok], x[ok] - xo[ok])
+    print("precision %d eps %g: max |x - oracle| %.3e, after H1 projection %.3e, null coordinate %.3e"
+          % (precision, eps, np.abs(x[ok] - xo[ok]).max(), np.abs(rem).max(), np.abs(null).max()))
     if precision == 1:
-        assert np.abs(x[ok] - xo[ok]).max() <= 1e-4
+        assert np.abs(rem).max() <= 1e-4 and np.abs(null).max() <= 1e-4
         return
-    # fp32 (production path).  The bar is 1e-3 per component.  e_y, e_psi, t and v are O(1) and meet it in absolute
-    # terms with a wide margin.  The curvature input kappa = tan(delta) / L reaches |kappa| = 6.47 and is barely
-    # determined by this QP (R[1] = 0: OSQP at eps 1e-3 and at eps 1e-5 differ by O(5) in kappa), so
-    # its fp32 round-off is judged relative to its magnitude: 1e-3 max(1, |kappa|), i.e. <= 1.2e-4 rad of steering.
-    err = np.abs(x[ok] - xo[ok])
+    # fp32 (production path), reference's own eps: every component within 1e-3 absolute, kappa (|kappa| up to 6.47, the
+    # QP's weakly determined input) included -- the bound rows are accumulated with a compensated sum for exactly this
+    assert np.abs(rem).max() <= QP_TOL, np.abs(rem).max()
+    assert np.abs(null).max() <= QP_TOL, np.abs(null).max()
     is_kappa = np.zeros(n, bool)
     is_kappa[3 * 31 + 1::2] = True
-    assert err[:, ~is_kappa].max() <= 2e-4, err[:, ~is_kappa].max()
-    assert (err[:, is_kappa] <= QP_TOL * np.maximum(1.0, np.abs(xo[ok][:, is_kappa]))).all(), err[:, is_kappa].max()
-    assert err.max() <= 2 * QP_TOL, err.max()
+    assert np.abs(x[ok] - xo[ok])[:, ~is_kappa].max() <= 2e-4
 
 
 def test_qp_fp64_kkt_certificate_at_full_batch(orc):
@@ -716,11 +718,14 @@ def test_qp_random_sample_vs_oracle():
     b = r["fp64_eps1e-05"]  # the north-star's parity setting: within 1e-3 of the oracle at eps 1e-5
     assert b["status_equal"] >= 0.995 and b["iters_equal"] >= 0.995
     assert max(b["same_trace_max_err_states_v"], b["same_trace_max_err_kappa"]) <= QP_TOL
+    assert b["same_trace_max_err_h1_projected"] <= QP_TOL and b["same_trace_max_h1_null_coordinate"] <= QP_TOL
     c = r["fp32_eps0.001"]
     assert c["status_equal"] >= 0.995, c
     assert c["iters_equal_where_solved"] >= 0.995, c
     assert c["same_trace_max_err_states_v"] <= 5e-4, c
-    assert c["same_trace_max_rel_err_kappa"] <= 2 * QP_TOL, c   # kappa relative to max(1, |kappa|); see DESIGN.md section 5
+    # absolute bar on every component after the H1 projection, null coordinate separately
+    assert c["same_trace_max_err_h1_projected"] <= QP_TOL, c
+    assert c["same_trace_max_h1_null_coordinate"] <= QP_TOL, c
 
 
 def test_synthetic_track_other_geometry(orc):

@@ -7,7 +7,7 @@ import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "tests"))
 import torch, mpc_b200
-from conftest import Track, fixed_pattern, sim_cfg
+from conftest import Track, fixed_pattern, h1_split, sim_cfg
 from oracle import oracle as orc
 
 
@@ -62,7 +62,11 @@ def compare(n=1024, seed=5):
         diff = (st == sto) & (it != ito) & (sto == 1)
         e3 = np.abs(x[diff] - xo[diff]) if diff.any() else np.zeros((1, 153))
         relk = e2[:, is_kappa] / np.maximum(1.0, np.abs(xo[same][:, is_kappa]))
-        extra = dict(same_trace=float(same.mean()), same_trace_max_err_states_v=float(e2[:, ~is_kappa].max()),
+        rem, null = h1_split(30, Pd[same], Ax[same], x[same] - xo[same])
+        extra = dict(same_trace_max_err_h1_projected=float(np.abs(rem).max()),
+                     same_trace_p999_err_h1_projected=float(np.quantile(np.abs(rem).max(axis=1), 0.999)),
+                     same_trace_max_h1_null_coordinate=float(np.abs(null).max()),
+                     same_trace=float(same.mean()), same_trace_max_err_states_v=float(e2[:, ~is_kappa].max()),
                      same_trace_max_err_kappa=float(e2[:, is_kappa].max()), same_trace_max_rel_err_kappa=float(relk.max()),
                      same_trace_p999_rel_err_kappa=float(np.quantile(relk.max(axis=1), 0.999)),
                      n_solved_other_iters=int(diff.sum()), other_iters_max_err=float(e3.max()),
