@@ -17,6 +17,10 @@ from conftest import fixed_pattern, h1_split, load_golden, sim_cfg, ulps
 
 pytestmark = pytest.mark.gpu
 QP_TOL = 1e-3  # north_star: per-instance max-norm
+# BASELINE configs[3] "time-optimal driving weights" are build-defined (bench.py::TIMEOPT): tracking
+# weight kept, the speed penalty cut to a fifth, a terminal TIME penalty added (chosen in the oracle so that every car
+# completes its lap: with QN[2] >= 1 the reference's algorithm itself drives 8 % of 256 cars into N-1 infeasible QPs in a row)
+TIMEOPT_Q, TIMEOPT_R, TIMEOPT_QN = [1.0, 0.0, 0.0], [0.1, 0.0], [1.0, 0.0, 0.3]
 
 
 def _dev():
@@ -666,7 +670,7 @@ def test_c4_full_size_time_optimal_n50(engine_factory, track, orc, orc_path):
     bit) and a sample of the first step is checked against the oracle."""
     from mpc_b200 import distributed as D
     N, half, B = 50, 131072, 262144
-    Q, R, QN = [0.1, 0.0, 0.0], [0.01, 0.0], [0.1, 0.0, 5.0]
+    Q, R, QN = TIMEOPT_Q, TIMEOPT_R, TIMEOPT_QN
     sc = D.make_scenarios(track.n_wp, half, seed=4)
     st = _start_states(track, sc)
     st2 = np.ascontiguousarray(np.concatenate([st, st], axis=1))
@@ -695,9 +699,76 @@ def test_c4_full_size_time_optimal_n50(engine_factory, track, orc, orc_path):
         assert r["qp_status"] == o1["qp_status"][b], (b, r["qp_status"], o1["qp_status"][b])
         if r["qp_status"] == 1:
             n_solved += 1
-            assert abs(r["iters"] - o1["iters"][b]) <= 25, (b, r["iters"], o1["iters"][b])  # fp32: at most one check apart
-            assert np.abs(r["u"] - o1["u"][b]).max() <= 10 * QP_TOL
+            assert r["iters"] == o1["iters"][b], (b, r["iters"], o1["iters"][b])
+            assert np.abs(r["u"] - o1["u"][b]).max() <= QP_TOL, (b, np.abs(r["u"] - o1["u"][b]).max())
     assert n_solved >= 6
+
+
+def test_c4_lap_follows_the_oracle(engine_factory, track, orc, orc_path):
+    """BASELINE configs[3] along a whole lap: 24 cars, time-optimal weights, N = 50, from the start line until every car has
+    crossed the finish line.  (a) The fp64 path free-running against the oracle free-running: same pose, previous plan and
+    infeasibility counter after EVERY step (the solver trace is then identical too: a different iteration count or status
+    would show in the plan).  (b) The fp32 production path teacher-forced from the oracle's state every 25th step: same
+    status; where OSQP solves, the same iteration count (a borderline check may fall one check later) and u within 1e-3.  The lap itself must make physical sense:
+    every car finishes, nobody leaves the corridor."""
+    N, B = 50, 24
+    Q, R, QN = TIMEOPT_Q, TIMEOPT_R, TIMEOPT_QN
+    rng = np.random.default_rng(4)
+    ey, ep = rng.uniform(-0.03, 0.03, B), rng.uniform(-0.05, 0.05, B)
+    x0, y0, p0 = track.wp_x[0], track.wp_y[0], track.wp_psi[0]
+    st0 = np.ascontiguousarray(np.stack([x0 - ey * np.sin(p0), y0 + ey * np.cos(p0), p0 + ep, np.zeros(B)]))
+    kmax = np.tan(0.66) / 0.12
+    cfg = orc.mpc_cfg(N, Q, R, QN, [-np.inf] * 3, [np.inf] * 3, [0.0, -kmax], [1.0, kmax], 4.0, 0.12, 0.06 / np.sqrt(2))
+    world = orc.World(orc_path, cfg, track.grid.shape, track.origin, track.res, 0.05)
+    orc.set_pow_mode(False)
+    e64 = engine_factory(grid="free", N=N, precision=1, Q=Q, R=R, QN=QN)
+    e32 = engine_factory(grid="free", N=N, precision=0, Q=Q, R=R, QN=QN)
+    e64.scenarios_init(st0)
+    e32.scenarios_init(st0)
+    st = np.ascontiguousarray(st0.T.copy()); ctrl = np.zeros((B, 2 * N)); inf = np.zeros(B, np.int32); alive = np.ones(B, np.int32)
+    finished = np.zeros(B, bool)
+    worst_pose = worst_plan = worst_u32 = 0.0
+    n_tf = n_tf_solved = n_other = fallbacks = 0
+    max_ey = 0.0
+    for k in range(400):
+        live = alive.astype(bool) & ~finished
+        if not live.any():
+            break
+        if k % 25 == 0:  # (b) fp32, teacher-forced from the oracle's current state
+            e32.scenarios_set_state(np.ascontiguousarray(st.T), ctrl, inf)
+            e32.step()
+            o32 = e32.scenarios_read()
+            for b in np.nonzero(live)[0]:
+                r = world.step(track.grid, st[b], ctrl[b], int(inf[b]))
+                n_tf += 1
+                assert r["qp_status"] == o32["qp_status"][b], (k, b, r["qp_status"], o32["qp_status"][b])
+                if r["qp_status"] == 1:
+                    n_tf_solved += 1
+                    if r["iters"] == o32["iters"][b]:
+                        worst_u32 = max(worst_u32, float(np.abs(r["u"] - o32["u"][b]).max()))
+                    else:  # a borderline termination check falls on the other side in fp32: one check apart, never more
+                        assert abs(r["iters"] - o32["iters"][b]) <= 25, (k, b, r["iters"], o32["iters"][b])
+                        n_other += 1
+        stt = world.batch_closed_loop(track.grid, st, ctrl, inf, alive, 1)
+        fallbacks += int(stt[3])
+        e64.step()
+        o = e64.scenarios_read()
+        assert np.array_equal(o["infeas"][live], inf[live]), k
+        worst_pose = max(worst_pose, float(np.abs(o["state"].T[live] - st[live]).max()))
+        worst_plan = max(worst_plan, float(np.abs(o["control"][live] - ctrl[live]).max()))
+        assert worst_pose <= 1e-7 and worst_plan <= 1e-6, (k, worst_pose, worst_plan)
+        for b in np.nonzero(live)[0]:  # lateral deviation ~ distance to the nearest waypoint (0.05 m spacing)
+            max_ey = max(max_ey, float(np.hypot(track.wp_x - st[b, 0], track.wp_y - st[b, 1]).min()))
+        finished |= st[:, 3] >= track.length
+    e64.step()
+    assert ((e64.scenarios_read()["flags"] & 32) != 0).all()   # MPC_ST_FINISHED once s >= length (simulation.py:134)
+    print("C4 lap: %d steps, %d fallbacks, max |e_y| %.3f m, pose %.1e plan %.1e (fp64 vs oracle), fp32 teacher-forced: %d steps "
+          "(%d solved, %d one check apart), max |u - oracle| %.2e on identical traces"
+          % (k, fallbacks, max_ey, worst_pose, worst_plan, n_tf, n_tf_solved, n_other, worst_u32))
+    assert finished.all(), "every car finishes its lap with the build-defined time-optimal weights"
+    assert max_ey <= 0.23, max_ey                      # nobody leaves the 0.46 m corridor
+    assert n_tf_solved >= 0.8 * n_tf and worst_u32 <= QP_TOL, (n_tf, n_tf_solved, worst_u32)
+    assert n_other <= 0.1 * n_tf_solved, (n_other, n_tf_solved)
 
 
 def test_qp_random_sample_vs_oracle():
