@@ -47,6 +47,8 @@ extern "C" {
 /* per-scenario QP status: the OSQP status values the reference would see in dec.info.status_val */
 #define MPC_QP_SOLVED 1
 #define MPC_QP_SOLVED_INACCURATE 2 /* max_iter reached, residuals within 10x tolerances */
+#define MPC_QP_PRIMAL_INFEASIBLE_INACCURATE 3 /* max_iter reached, certificate within 10x tolerances: no solution (NaN) */
+#define MPC_QP_DUAL_INFEASIBLE_INACCURATE 4
 #define MPC_QP_MAX_ITER (-2)
 #define MPC_QP_PRIMAL_INFEASIBLE (-3)
 #define MPC_QP_DUAL_INFEASIBLE (-4)

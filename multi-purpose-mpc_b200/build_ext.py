@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
         if p.wait() != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if force or procs or _newer(objs, OUT):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", OUT] + objs + ["-ccbin", "/usr/bin/g++"]
+        cmd = [nvcc] + ARCH + ["-shared", "-o", OUT] + objs + ["-ccbin", "/usr/bin/g++", "-ldl"]
         subprocess.check_call(cmd)
     return OUT
 

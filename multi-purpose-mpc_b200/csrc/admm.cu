@@ -1,5 +1,6 @@
 // admm.cu -- kernel entry points for K1+K2 (see admm.cuh).  FMA contraction is enabled here: the QP
 // solution is compared within a tolerance, not bit-for-bit.
+#include "launch_util.h"
 #include "engine.h"
 #include "admm_epilogue.cuh"
 #include <cstdio>
@@ -37,7 +38,7 @@ __device__ __forceinline__ void control_epilogue(Comm& cm, const MpcParams& mp, 
                                                  double* cc, int* infeas, double* u_out, int* iters, int* qp_status,
                                                  int* flags, int b, int fl, const RolloutArgs& ro) {
     const int N = mp.N;
-    const bool ok = !(r.status == -3 || r.status == -4 || r.status == -7);  // OSQP returns x (MPC.py:185-206)
+    const bool ok = !(r.status == -3 || r.status == -4 || r.status == -7 || r.status == 3 || r.status == 4);  // OSQP returns x (MPC.py:185-206)
     int inf = infeas[b];
     cm.sync();
     if (ok) {
@@ -186,7 +187,7 @@ static void solve_qp_launch(int N, const AdmmSettings& st, const double* Pd, con
     constexpr int R = clamp_rlev<NLEV, RLEV>();
     const int grid = (B + kWarpsPerBlock - 1) / kWarpsPerBlock, block = 32 * kWarpsPerBlock;
     const size_t smem = warp_smem_bytes<T, NLEV, R>();
-    cudaFuncSetAttribute(solve_qp_kernel<T, NLEV, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    { static int have_ = 0; ensure_dynamic_smem(solve_qp_kernel<T, NLEV, R, MINB>, have_, smem); }
     solve_qp_kernel<T, NLEV, R, MINB><<<grid, block, smem, s>>>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B);
 }
 
@@ -198,7 +199,7 @@ static void assemble_solve_launch(const MpcParams& mp, const AdmmSettings& st, c
     constexpr int R = clamp_rlev<NLEV, RLEV>();
     const int grid = (B + kWarpsPerBlock - 1) / kWarpsPerBlock, block = 32 * kWarpsPerBlock;
     const size_t smem = warp_smem_bytes<T, NLEV, R>();
-    cudaFuncSetAttribute(assemble_solve_kernel<T, NLEV, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    { static int have_ = 0; ensure_dynamic_smem(assemble_solve_kernel<T, NLEV, R, MINB>, have_, smem); }
     assemble_solve_kernel<T, NLEV, R, MINB><<<grid, block, smem, s>>>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas,
                                                                       u_out, x_out, iters, qp_status, flags, B, rs, Ts);
 }
@@ -208,7 +209,7 @@ static void solve_qp_block_launch(int N, const AdmmSettings& st, const double* P
                                   const double* l, const double* u, double* x_out, int* iters, int* status, int B,
                                   cudaStream_t s) {
     const size_t smem = block_smem_bytes<T, NLEV, NT>();
-    cudaFuncSetAttribute(solve_qp_block_kernel<T, NLEV, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    { static int have_ = 0; ensure_dynamic_smem(solve_qp_block_kernel<T, NLEV, NT>, have_, smem); }
     solve_qp_block_kernel<T, NLEV, NT><<<B, NT, smem, s>>>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B);
 }
 
@@ -218,7 +219,7 @@ static void assemble_solve_block_launch(const MpcParams& mp, const AdmmSettings&
                                         const double* lb, int* infeas, double* u_out, double* x_out, int* iters,
                                         int* qp_status, int* flags, int B, cudaStream_t s, double* rs, double Ts) {
     const size_t smem = block_smem_bytes<T, NLEV, NT>();
-    cudaFuncSetAttribute(assemble_solve_block_kernel<T, NLEV, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    { static int have_ = 0; ensure_dynamic_smem(assemble_solve_block_kernel<T, NLEV, NT>, have_, smem); }
     assemble_solve_block_kernel<T, NLEV, NT><<<B, NT, smem, s>>>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out,
                                                                 x_out, iters, qp_status, flags, B, rs, Ts);
 }
@@ -255,6 +256,7 @@ void preload_solve_kernels(int precision, int N) {
 
 int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax,
                     const double* l, const double* u, double* x_out, int* iters, int* status, int B, cudaStream_t s) {
+    NvtxRange nvtx_("mpc:K2 solve_qp");
 #define WARP_GO(T_, L_) solve_qp_launch<T_, L_, Tune<T_>::rlev, Tune<T_>::minb>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s)
 #define BLOCK_GO(T_, L_, NT_) solve_qp_block_launch<T_, L_, NT_>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s)
     const int ns = N + 1;
@@ -277,6 +279,7 @@ int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings
                           const double* spatial, const int* wp_id, double* control, const double* ub, const double* lb,
                           int* infeas, double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
                           cudaStream_t s, double* rollout_state, double Ts, const int* order, bool prefer_stage) {
+    NvtxRange nvtx_("mpc:K1+K2 assemble_solve");
 #define WARP_GO(T_, L_) assemble_solve_launch<T_, L_, Tune<T_>::rlev, Tune<T_>::minb>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts)
 #define BLOCK_GO(T_, L_, NT_) assemble_solve_block_launch<T_, L_, NT_>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts)
     const int ns = mp.N + 1;

@@ -497,8 +497,16 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
     int status = 0, iter = 0;
     int chk = st.check_termination > 0 ? st.check_termination : -1;
     int adp = st.adaptive_rho_interval > 0 ? st.adaptive_rho_interval : -1;
-    for (iter = 1; iter <= st.max_iter; ++iter) {
-        T g[5], td[3], tb[5], dl[5];
+    // phase 0 = iterating; after max_iter passes OSQP (osqp.c, after its main loop) runs a NORMAL termination check if
+    // the last pass was not a check pass (phase 1) and then the APPROXIMATE one (phase 2: every tolerance x 10, statuses
+    // 2 / 3 / 4), else reports max-iter (-2).  Both go through the same check code below.
+    int phase = 0;
+    T tol = T(1);
+    T dl[5] = {0, 0, 0, 0, 0}, ed[3] = {0, 0, 0}, eb[5] = {0, 0, 0, 0, 0};
+    for (iter = 1;; ++iter) {
+        bool can_check = true, can_adapt = false;
+        if (phase == 0) {
+        T g[5], td[3], tb[5];
 #pragma unroll
         for (int i = 0; i < 3; ++i) td[i] = rd * rdy[i];
 #pragma unroll
@@ -509,7 +517,7 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
         kkt_solve<T, NLEV, RLEV>(cm, f, g, lane, dl);
         T add[3], adb[5];
         A_apply(cm, s, dl, lane, add, adb);
-        T ed[3], eb[5];  // dual steps dy = rho ((v - z_prev) - (z_new - z_prev))
+        // ed, eb: dual steps dy = rho ((v - z_prev) - (z_new - z_prev))
 #pragma unroll
         for (int i = 0; i < 5; ++i) x[i] = tfma(alpha, dl[i], x[i]);
 #pragma unroll
@@ -535,9 +543,10 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
 #pragma unroll
             for (int i = 0; i < 5; ++i) ty[i] += dty[i];
         }
-        const bool can_check = (--chk == 0), can_adapt = (--adp == 0);
+        can_check = (--chk == 0); can_adapt = (--adp == 0);
         if (can_check) chk = st.check_termination;
         if (can_adapt) adp = st.adaptive_rho_interval;
+        }  // phase == 0
         if (can_check || can_adapt) {
             T axd[3], axb[5], aty[5], zd[3], D[5], Ed[3], Eb[5], Di[5], Edi[3], Ebi[5], dx[5], dyd[3], dyb[5];
 #pragma unroll
@@ -582,13 +591,13 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
             npx_s = cm.max(npx_s); npx_u = cm.max(npx_u); naty_s = cm.max(naty_s); naty_u = cm.max(naty_u);
             if (can_check) {
                 if (pr_u > T(kOsqpInfty) || du_u > T(kOsqpInfty)) { status = -7; break; }
-                const T eps_prim = T(st.eps_abs) + T(st.eps_rel) * tmax(nz_u, nax_u);
-                const T eps_dual = T(st.eps_abs) + T(st.eps_rel) * cinv * tmax(tmax(nq_u, naty_u), npx_u);
+                const T eps_prim = tol * (T(st.eps_abs) + T(st.eps_rel) * tmax(nz_u, nax_u));
+                const T eps_dual = tol * (T(st.eps_abs) + T(st.eps_rel) * cinv * tmax(tmax(nq_u, naty_u), npx_u));
                 const bool prim_ok = pr_u < eps_prim, dual_ok = du_u < eps_dual;
-                if (prim_ok && dual_ok) { status = 1; break; }
+                if (prim_ok && dual_ok) { status = phase == 2 ? 2 : 1; break; }
                 bool pinf = false, dinf = false;
                 if (!prim_ok) {  // is_primal_infeasible
-                    const T epi = T(st.eps_prim_inf);
+                    const T epi = tol * T(st.eps_prim_inf);
                     T pyb[5], ndy = 0, lhs = 0;
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
@@ -616,7 +625,7 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
                     }
                 }
                 if (!dual_ok && !pinf) {  // is_dual_infeasible
-                    const T edi = T(st.eps_dual_inf);
+                    const T edi = tol * T(st.eps_dual_inf);
                     T ndx = 0, qdx = 0;
 #pragma unroll
                     for (int i = 0; i < 5; ++i) { ndx = tmax(ndx, tabs(D[i] * dx[i])); qdx += s.q[i] * dx[i]; }
@@ -645,8 +654,8 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
                         }
                     }
                 }
-                if (pinf) { status = -3; break; }
-                if (dinf) { status = -4; break; }
+                if (pinf) { status = phase == 2 ? 3 : -3; break; }
+                if (dinf) { status = phase == 2 ? 4 : -4; break; }
             }
             if (can_adapt) {  // adapt_rho / compute_rho_estimate on the scaled residuals
                 T pn = pr_s / (tmax(nz_s, nax_s) + T(1e-10));
@@ -660,41 +669,20 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
                 }
             }
         }
+        if (phase == 2) { status = -2; break; }
+        if (phase == 1 || (phase == 0 && iter >= st.max_iter)) {
+            // the last pass was a check pass iff check_termination divides max_iter
+            const bool checked = phase == 0 && st.check_termination > 0 && (st.max_iter % st.check_termination == 0);
+            phase = (phase == 1 || checked) ? 2 : 1;
+            if (phase == 2) tol = T(10);
+        }
     }
     T D[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) D[i] = sm[(3 + i) * W + lane];
-    if (status == 0) {
-        // max_iter reached: OSQP re-checks the residuals with 10x looser tolerances ("approximate"
-        // termination) and reports solved-inaccurate (2) or max-iter (-2).  Either way it RETURNS
-        // the iterate, which is all the reference looks at (MPC.py:185-206).
-        iter = st.max_iter;
-        T axd[3], axb[5], aty[5];
-        A_apply(cm, s, x, lane, axd, axb);
-#pragma unroll
-        for (int i = 0; i < 5; ++i) aty[i] = ty[i];
-        T pr_u = 0, nz_u = 0, nax_u = 0, du_u = 0, npx_u = 0, naty_u = 0;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const T ei = sm[(21 + i) * W + lane], zdi = sm[i * W + lane];
-            pr_u = tmax(pr_u, tabs(axd[i] - zdi) * ei); nz_u = tmax(nz_u, tabs(zdi) * ei);
-            nax_u = tmax(nax_u, tabs(axd[i]) * ei);
-        }
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const T ei = sm[(24 + i) * W + lane], di = sm[(16 + i) * W + lane], px = s.P[i] * x[i];
-            pr_u = tmax(pr_u, tabs(axb[i] - zb[i]) * ei); nz_u = tmax(nz_u, tabs(zb[i]) * ei);
-            nax_u = tmax(nax_u, tabs(axb[i]) * ei);
-            du_u = tmax(du_u, tabs(px + s.q[i] + aty[i]) * di); npx_u = tmax(npx_u, tabs(px) * di);
-            naty_u = tmax(naty_u, tabs(aty[i]) * di);
-        }
-        pr_u = cm.max(pr_u); nz_u = cm.max(nz_u); nax_u = cm.max(nax_u);
-        du_u = cm.max(du_u) * cinv; npx_u = cm.max(npx_u); naty_u = cm.max(naty_u);
-        const T eps_prim = T(10) * T(st.eps_abs) + T(10) * T(st.eps_rel) * tmax(nz_u, nax_u);
-        const T eps_dual = T(10) * T(st.eps_abs) + T(10) * T(st.eps_rel) * cinv * tmax(tmax(nq_u, naty_u), npx_u);
-        status = (pr_u < eps_prim && du_u < eps_dual) ? 2 : -2;
-    }
-    const bool nan_out = (status == -3 || status == -4 || status == -7);
+    if (phase != 0) iter = st.max_iter;
+    // OSQP stores no solution for the (approximately) infeasible and the non-convex statuses (NaN vectors)
+    const bool nan_out = (status == -3 || status == -4 || status == -7 || status == 3 || status == 4);
 #pragma unroll
     for (int i = 0; i < 5; ++i) w[i] = nan_out ? T(NAN) : D[i] * x[i];
     SolveResult r;

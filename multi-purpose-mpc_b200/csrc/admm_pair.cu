@@ -1,5 +1,6 @@
 // admm_pair.cu -- kernel entry points of the paired-stage fp32 production path (see admm_pair.cuh).  FMA contraction
 // is enabled here: the QP solution is compared within a tolerance, not bit-for-bit.
+#include "launch_util.h"
 #include "engine.h"
 #include "admm_epilogue.cuh"
 #include "admm_pair.cuh"
@@ -42,7 +43,7 @@ __device__ __forceinline__ void control_epilogue2(const GroupComm<LPS>& cm, cons
                                                   const SolveResult& r, double* cc, int* infeas, double* u_out, int* iters,
                                                   int* qp_status, int* flags, int b, int fl, const RolloutArgs& ro) {
     const int N = mp.N, gl = cm.gl, kA = 2 * gl, kB = kA + 1;
-    const bool ok = !(r.status == -3 || r.status == -4 || r.status == -7);  // OSQP returns x (MPC.py:185-206)
+    const bool ok = !(r.status == -3 || r.status == -4 || r.status == -7 || r.status == 3 || r.status == 4);  // OSQP returns x (MPC.py:185-206)
     int inf = infeas[b];
     if (ok) {
         if (kA < N) { cc[2 * kA] = (double)w[3].x; cc[2 * kA + 1] = atan((double)w[4].x * mp.L); }  // MPC.py:187-189
@@ -165,7 +166,7 @@ static void solve_qp_pair_launch(int N, const AdmmSettings& st, const double* Pd
                                  cudaStream_t s) {
     constexpr int per_block = kPairWarpsPerBlock * (32 / LPS);
     const size_t smem = pair_smem_bytes<LPS>();
-    cudaFuncSetAttribute(solve_qp_pair_kernel<LPS, kPairMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    { static int have_ = 0; ensure_dynamic_smem(solve_qp_pair_kernel<LPS, kPairMinBlocks>, have_, smem); }
     solve_qp_pair_kernel<LPS, kPairMinBlocks><<<(B + per_block - 1) / per_block, 32 * kPairWarpsPerBlock, smem, s>>>(
         N, st, make_float2((float)st.alpha, (float)st.alpha), make_float2(-(float)st.alpha, -(float)st.alpha), Pd, q, Ax, l, u,
         x_out, iters, status, B);
@@ -179,8 +180,7 @@ static void assemble_solve_pair_launch(const MpcParams& mp, const AdmmSettings& 
                                        const int* order) {
     constexpr int per_block = kPairWarpsPerBlock * (32 / LPS);
     const size_t smem = pair_smem_bytes<LPS>();
-    cudaFuncSetAttribute(assemble_solve_pair_kernel<LPS, LOOSE, kPairMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
+    { static int have_ = 0; ensure_dynamic_smem(assemble_solve_pair_kernel<LPS, LOOSE, kPairMinBlocks>, have_, smem); }
     assemble_solve_pair_kernel<LPS, LOOSE, kPairMinBlocks><<<(B + per_block - 1) / per_block, 32 * kPairWarpsPerBlock, smem, s>>>(
         mp, st, make_float2((float)st.alpha, (float)st.alpha), make_float2(-(float)st.alpha, -(float)st.alpha), pv, spatial, wp_id,
         control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, rs, Ts, order);
@@ -196,6 +196,7 @@ void preload_pair_kernels(int N) {
 
 int launch_solve_qp_pair(int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax, const double* l,
                          const double* u, double* x_out, int* iters, int* status, int B, cudaStream_t s) {
+    NvtxRange nvtx_("mpc:K2 solve_qp (paired fp32)");
     const int ns = N + 1;
     if (ns > 64) return MPC_E_UNSUPPORTED;
     if (ns <= 16) solve_qp_pair_launch<8>(N, st, Pd, q, Ax, l, u, x_out, iters, status, B, s);
@@ -208,6 +209,7 @@ int launch_assemble_solve_pair(const MpcParams& mp, const AdmmSettings& st, cons
                                const int* wp_id, double* control, const double* ub, const double* lb, int* infeas,
                                double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B, cudaStream_t s,
                                double* rollout_state, double Ts, const int* order) {
+    NvtxRange nvtx_("mpc:K1+K2 assemble_solve (paired fp32)");
     const int ns = mp.N + 1;
     if (ns > 64) return MPC_E_UNSUPPORTED;
     // e_psi and t unbounded (the reference's StateConstraints): OSQP's "loose" rows, skipped by the loop

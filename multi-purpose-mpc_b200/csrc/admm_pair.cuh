@@ -584,7 +584,7 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
     int adp = st.adaptive_rho_interval > 0 ? st.adaptive_rho_interval : -1;
     auto finish = [&](int status, int it) {
         f2 w[5];
-        const bool nan_out = (status == -3 || status == -4 || status == -7);
+        const bool nan_out = (status == -3 || status == -4 || status == -7 || status == 3 || status == 4);  // OSQP: no solution
 #pragma unroll
         for (int i = 0; i < 5; ++i) w[i] = nan_out ? bc(NAN) : pmul(sm[(3 + i) * LPS + gl], x[i]);
         SolveResult r;
@@ -652,10 +652,18 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
         At_apply2<LPS, LOOSE>(cm, s, ed, eb, u, u);
     };
     // termination check / rho adaptation after a pass; returns true when every scenario of the warp is done
+    // phase 0 = iterating.  After max_iter passes OSQP (osqp.c, after its main loop) runs a NORMAL termination check if the
+    // last pass was not a check pass (phase 1), then the APPROXIMATE one (phase 2: every tolerance x 10, statuses 2 / 3 / 4),
+    // else reports max-iter (-2); both go through this same check code.
+    int phase = 0;
+    float tol = 1.0f;
     auto after_pass = [&]() __attribute__((always_inline)) -> bool {
-        const bool can_check = (--chk == 0), can_adapt = (--adp == 0);
-        if (can_check) chk = st.check_termination;
-        if (can_adapt) adp = st.adaptive_rho_interval;
+        bool can_check = true, can_adapt = false;
+        if (phase == 0) {
+            can_check = (--chk == 0); can_adapt = (--adp == 0);
+            if (can_check) chk = st.check_termination;
+            if (can_adapt) adp = st.adaptive_rho_interval;
+        }
         if (can_check || can_adapt) {
             f2 axd[3], axb[5], zd[3], Di[5], Edi[3], Ebi[5];
 #pragma unroll
@@ -699,14 +707,14 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
             if (can_check) {
                 int status = 0;
                 if (pr_u > (float)kOsqpInfty || du_u > (float)kOsqpInfty) status = -7;
-                const float eps_prim = (float)st.eps_abs + (float)st.eps_rel * fmaxf(nz_u, nax_u);
-                const float eps_dual = (float)st.eps_abs + (float)st.eps_rel * cinv * fmaxf(fmaxf(nq_u, naty_u), npx_u);
+                const float eps_prim = tol * ((float)st.eps_abs + (float)st.eps_rel * fmaxf(nz_u, nax_u));
+                const float eps_dual = tol * ((float)st.eps_abs + (float)st.eps_rel * cinv * fmaxf(fmaxf(nq_u, naty_u), npx_u));
                 const bool prim_ok = pr_u < eps_prim, dual_ok = du_u < eps_dual;
-                if (status == 0 && prim_ok && dual_ok) status = 1;
+                if (status == 0 && prim_ok && dual_ok) status = phase == 2 ? 2 : 1;
                 const bool open = !done && status == 0;  // this scenario still needs the certificates
                 bool pinf = false, dinf = false;
                 if (GC::warp_any(open && !prim_ok)) {  // is_primal_infeasible
-                    const float epi = (float)st.eps_prim_inf;
+                    const float epi = tol * (float)st.eps_prim_inf;
                     f2 pyb[5];
                     float ndy = 0, lhs = 0;
 #pragma unroll
@@ -747,7 +755,7 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
                     }
                 }
                 if (GC::warp_any(open && !dual_ok && !pinf)) {  // is_dual_infeasible (dx = alpha D of this iteration)
-                    const float edi = (float)st.eps_dual_inf;
+                    const float edi = tol * (float)st.eps_dual_inf;
                     float ndx = 0, qdx = 0, npdx = 0;
 #pragma unroll
                     for (int i = 0; i < 5; ++i) {
@@ -781,9 +789,10 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
                         dinf = cand && !cm.any(bad != 0);
                     }
                 }
-                if (status == 0 && pinf) status = -3;
-                if (status == 0 && dinf) status = -4;
-                if (!done && status != 0) finish(status, iter);
+                if (status == 0 && pinf) status = phase == 2 ? 3 : -3;
+                if (status == 0 && dinf) status = phase == 2 ? 4 : -4;
+                if (status == 0 && phase == 2) status = -2;
+                if (!done && status != 0) finish(status, phase ? st.max_iter : iter);
                 if (GC::warp_all(done)) return true;
             }
             if (can_adapt) {  // adapt_rho / compute_rho_estimate on the scaled residuals
@@ -821,37 +830,15 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
         }
         return false;
     };
-    for (iter = 1; iter <= st.max_iter; ++iter) {
-        pass(iter == 1);
-        if (after_pass()) break;
-    }
-    if (GC::warp_any(!done)) {
-        // max_iter reached: OSQP re-checks the residuals with 10x looser tolerances and reports
-        // solved-inaccurate (2) or max-iter (-2); either way it RETURNS the iterate (MPC.py:185-206).
-        f2 axd[3], axb[5];
-        A_apply2<LPS, LOOSE>(cm, s, x, axd, axb);
-        if (LOOSE) {
-            axb[1] = pmul(ldsv(&sm[35 * LPS + gl]), x[1]); axb[2] = pmul(ldsv(&sm[36 * LPS + gl]), x[2]);
-            zb[1] = axb[1]; zb[2] = axb[2];
+    for (iter = 1;; ++iter) {
+        if (phase == 0) pass(iter == 1);
+        if (after_pass()) break;   // phase 2 always ends here: every scenario still open is finished with -2
+        if (phase == 1 || (phase == 0 && iter >= st.max_iter)) {
+            // the last pass was a check pass iff check_termination divides max_iter
+            const bool checked = phase == 0 && st.check_termination > 0 && (st.max_iter % st.check_termination == 0);
+            phase = (phase == 1 || checked) ? 2 : 1;
+            if (phase == 2) tol = 10.0f;
         }
-        float pr_u = 0, nz_u = 0, nax_u = 0, du_u = 0, npx_u = 0, naty_u = 0;
-        const float nq_u = ldsv(&sm[54 * LPS + gl]).y, cinv = ldsv(&sm[55 * LPS + gl]).y;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const f2 ei = ldsv(&sm[(21 + i) * LPS + gl]), zdi = ldsv(&sm[i * LPS + gl]);
-            amax(pr_u, pmul(psub(axd[i], zdi), ei)); amax(nz_u, pmul(zdi, ei)); amax(nax_u, pmul(axd[i], ei));
-        }
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const f2 ei = ldsv(&sm[(24 + i) * LPS + gl]), di = ldsv(&sm[(16 + i) * LPS + gl]), px = pmul(ldsv(&sm[(49 + i) * LPS + gl]), x[i]);
-            amax(pr_u, pmul(psub(axb[i], zb[i]), ei)); amax(nz_u, pmul(zb[i], ei)); amax(nax_u, pmul(axb[i], ei));
-            amax(du_u, pmul(padd(px, u[i]), di)); amax(npx_u, pmul(px, di)); amax(naty_u, pmul(psub(u[i], ldsv(&sm[(29 + i) * LPS + gl])), di));
-        }
-        pr_u = cm.max(pr_u); nz_u = cm.max(nz_u); nax_u = cm.max(nax_u);
-        du_u = cm.max(du_u) * cinv; npx_u = cm.max(npx_u); naty_u = cm.max(naty_u);
-        const float eps_prim = 10.0f * (float)st.eps_abs + 10.0f * (float)st.eps_rel * fmaxf(nz_u, nax_u);
-        const float eps_dual = 10.0f * (float)st.eps_abs + 10.0f * (float)st.eps_rel * cinv * fmaxf(fmaxf(nq_u, naty_u), npx_u);
-        if (!done) finish((pr_u < eps_prim && du_u < eps_dual) ? 2 : -2, st.max_iter);
     }
 }
 

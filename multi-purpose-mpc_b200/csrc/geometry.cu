@@ -6,6 +6,7 @@
 // Reference: src/reference_path.py:206-287 (static width), 466-648 (update_path_constraints),
 // src/map.py:77-137 (w2m, m2w, add_obstacles), src/spatial_bicycle_models.py:183-279 (t2s, drive,
 // get_current_waypoint); skimage.draw.line_aa cell order restated from skimage/draw/_draw.pyx.
+#include "launch_util.h"
 #include "engine.h"
 #include <cstdlib>
 
@@ -82,7 +83,8 @@ __global__ void rasterize_kernel(const uint32_t* __restrict__ base, uint32_t* __
 
 void launch_rasterize(const uint32_t* base, uint32_t* grids, int words, const GridView& g, const int* obs_px,
                       const int* offsets, int B, cudaStream_t st) {
-    cudaFuncSetAttribute(rasterize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, words * 4);
+    NvtxRange nvtx_("mpc:rasterize");
+    { static int have_ = 0; ensure_dynamic_smem(rasterize_kernel, have_, (size_t)words * 4); }
     rasterize_kernel<<<B, 256, words * 4, st>>>(base, grids, words, g, obs_px, offsets);
 }
 
@@ -144,6 +146,7 @@ __global__ void compute_width_kernel(const uint32_t* __restrict__ grid, GridView
 
 void launch_compute_width(const uint32_t* grid, const GridView& g, const PathView& pv, double max_width, double* ub,
                           double* lb, double* border, int* err, cudaStream_t st) {
+    NvtxRange nvtx_("mpc:K3b compute_width");
     const int warps = 2 * pv.n_wp;
     compute_width_kernel<<<(warps * 32 + 127) / 128, 128, 0, st>>>(grid, g, pv, max_width, ub, lb, border, err);
 }
@@ -328,6 +331,7 @@ __global__ void build_ray_table_kernel(GridView g, PathView pv, uint32_t* __rest
 
 void launch_build_ray_table(const GridView& g, const PathView& pv, uint32_t* cells, int* len, int max_len,
                             cudaStream_t st) {
+    NvtxRange nvtx_("mpc:build_ray_table");
     build_ray_table_kernel<<<(pv.n_wp + 127) / 128, 128, 0, st>>>(g, pv, cells, len, max_len);
 }
 
@@ -684,6 +688,7 @@ void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridV
                     double sm, double* ub, double* lb, double* cells_sm, int* flags, int B, bool rowspan_ok,
                     cudaStream_t st, const double* state, int* wp_id_out, double* spatial_out, double length,
                     const int* prev_iters, int* order_out, int* long_out, unsigned char* bucket_of) {
+    NvtxRange nvtx_("mpc:K3 raycast");
     RaycastArgs a;
     a.prev_iters = prev_iters; a.order_out = (order_out && bucket_of) ? order_out : nullptr; a.long_out = long_out; a.bucket_of = bucket_of;
     a.state = state; a.wp_id_out = wp_id_out; a.spatial_out = spatial_out; a.length = length;
@@ -697,16 +702,16 @@ void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridV
     a.stage_rows = stage_rows;
     const int ctas_needed = (B + warps - 1) / warps;
     // persistent-style grid: enough CTAs to fill the machine a few times over, each looping over scenarios
-    const int max_ctas = 148 * 8;
+    const int max_ctas = sm_count() * 8;
     const int grid = (ctas_needed < max_ctas ? ctas_needed : max_ctas) + (a.order_out ? 1 : 0);
     if (mode == 1) {
-        cudaFuncSetAttribute(raycast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        { static int have_ = 0; ensure_dynamic_smem(raycast_kernel<1>, have_, smem); }
         raycast_kernel<1><<<grid, warps * 32, smem, st>>>(a);
     } else if (mode == 2) {
-        cudaFuncSetAttribute(raycast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        { static int have_ = 0; ensure_dynamic_smem(raycast_kernel<2>, have_, smem); }
         raycast_kernel<2><<<grid, warps * 32, smem, st>>>(a);
     } else {
-        cudaFuncSetAttribute(raycast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        { static int have_ = 0; ensure_dynamic_smem(raycast_kernel<0>, have_, smem); }
         raycast_kernel<0><<<grid, warps * 32, smem, st>>>(a);
     }
 }
@@ -716,6 +721,7 @@ void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridV
 // ------------------------------------------------------------------------------------------------
 void launch_localize(const double* state, int* wp_id, double* spatial, int* flags, const PathView& pv, double length,
                      int B, cudaStream_t st) {
+    NvtxRange nvtx_("mpc:K4a localize_t2s");
     localize_t2s_kernel<<<(B + 255) / 256, 256, 0, st>>>(state, wp_id, spatial, flags, pv, length, B);
 }
 
@@ -743,6 +749,7 @@ __global__ void rollout_kernel(double* __restrict__ state, const double* __restr
 
 void launch_rollout(double* state, const double* spatial, const int* wp_id, const double* u, const int* flags,
                     const PathView& pv, double L, double Ts, int B, cudaStream_t st) {
+    NvtxRange nvtx_("mpc:K4b rollout");
     rollout_kernel<<<(B + 255) / 256, 256, 0, st>>>(state, spatial, wp_id, u, flags, pv, L, Ts, B);
 }
 
@@ -771,6 +778,7 @@ __global__ void predict_xy_kernel(const double* __restrict__ x_sol, const int* _
 }
 
 void launch_predict_xy(const double* x_sol, const int* wp_id, const PathView& pv, int N, double* xy, int B, cudaStream_t st) {
+    NvtxRange nvtx_("mpc:predict_xy");
     const long n = (long)B * (N - 2);
     if (n <= 0) return;
     predict_xy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_sol, wp_id, pv, N, xy, B);
@@ -792,6 +800,7 @@ __global__ void accumulate_stats_kernel(const int* __restrict__ flags, const int
 
 void launch_accumulate_stats(const int* flags, const int* iters, const double* spatial, double* acc, int B,
                              cudaStream_t st) {
+    NvtxRange nvtx_("mpc:accumulate_stats");
     accumulate_stats_kernel<<<(B + 255) / 256, 256, 0, st>>>(flags, iters, spatial, acc, B);
 }
 

@@ -18,7 +18,7 @@ sys.path.insert(0, REPO)
 from oracle import oracle as orc  # noqa: E402
 from oracle import ref_harness as rh  # noqa: E402
 
-OUT = os.path.join(REPO, "tests", "golden")
+OUT = os.environ.get("MPC_GOLDEN_OUT") or os.path.join(REPO, "tests", "golden")   # MPC_GOLDEN_OUT: write elsewhere (live test)
 
 
 def fixed_pattern(N):

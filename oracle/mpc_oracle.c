@@ -14,7 +14,7 @@
  * from the published algorithms and validated only through (a) the reference's own Python control
  * flow run on top of them (oracle/make_golden.py) and (b) solver-independent certificates (KKT
  * residuals, line invariants).  Everything that is pure numpy in the reference is checked against
- * the reference's own code imported under shims (tests/test_oracle_vs_reference_golden.py).
+ * the reference's own code imported under shims (tests/test_oracle_vs_reference_live.py re-generates the fixtures when /root/reference is present; tests/test_oracle_cpu.py checks this file against them).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * call into this file.  The product (multi-purpose-mpc_b200/) never does.

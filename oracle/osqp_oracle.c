@@ -481,11 +481,20 @@ int orc_osqp_solve(int n, int m, const int *Pp, const int *Pi, const double *Px_
             }
         }
     }
-    if (!status) { /* max_iter reached */
+    if (!status) { /* max_iter reached (osqp.c, after the main loop) */
         iter = s->max_iter;
         pri_res = compute_pri_res(w, s->scaling > 0);
         dua_res = compute_dua_res(w, s->scaling > 0);
-        status = check_termination(w, s, pri_res, dua_res, 1);
+        /* "if (!can_check_termination) { update_info(...); check_termination(work, 0); }": when the last iteration was not
+         * a check iteration (max_iter not a multiple of check_termination, or checks disabled) OSQP first runs a NORMAL
+         * termination check on the final iterate ... */
+        if (!(s->check_termination && (s->max_iter % s->check_termination == 0))) {
+            ++n_checks;
+            status = check_termination(w, s, pri_res, dua_res, 0);
+        }
+        /* ... and only if that leaves the problem unsolved the approximate one (10x tolerances; it can also return the
+         * inaccurate infeasibility statuses 3 / 4), else OSQP_MAX_ITER_REACHED */
+        if (!status) status = check_termination(w, s, pri_res, dua_res, 1);
         if (!status) status = OSQP_MAX_ITER_REACHED;
     }
 finish:

@@ -53,7 +53,7 @@ def test_qp_matches_oracle(orc, precision, eps):
     eng.close()
     assert np.array_equal(st, sto), "status differs from the oracle"
     assert np.array_equal(it, ito), "iteration counts differ from the oracle"
-    ok = ~np.isin(sto, (-3, -4, -7))                    # OSQP returns an iterate (also for max-iter, -2)
+    ok = ~np.isin(sto, (-3, -4, -7, 3, 4))                    # OSQP returns an iterate (also for max-iter, -2)
     assert ok.sum() >= 60 and (~ok).sum() >= 6          # the fixture contains infeasible QPs too
     assert np.isnan(x[~ok]).all() and np.isnan(xo[~ok]).all()   # no solution there (MPC.py:208 path)
     # the zero-cost direction (u_{N-1}.kappa, x_N.e_psi) is projected out of x - x_oracle, the remainder
@@ -587,7 +587,7 @@ def test_qp_non_default_osqp_settings(orc, precision, settings):
         same = it[solved] == ito[solved]
         assert same.all() if settings.get("rho", 0.1) <= 0.1 else same.mean() >= 0.9
         assert (st == sto).mean() >= 0.9
-    ok = ~np.isin(sto, (-3, -4, -7)) & ~np.isin(st, (-3, -4, -7)) & (st == sto) & (it == ito)
+    ok = ~np.isin(sto, (-3, -4, -7, 3, 4)) & ~np.isin(st, (-3, -4, -7, 3, 4)) & (st == sto) & (it == ito)
     if ok.any():
         err = np.abs(x[ok] - xo[ok])
         is_kappa = np.zeros(n, bool)
@@ -595,6 +595,40 @@ def test_qp_non_default_osqp_settings(orc, precision, settings):
         assert err[:, ~is_kappa].max() <= (1e-4 if precision == 1 else 1e-3), err[:, ~is_kappa].max()
         if precision == 1:
             assert err.max() <= 1e-4
+
+
+@pytest.mark.parametrize("precision,settings,expect", [
+    (1, dict(max_iter=60), (1, 60)),                                  # exact check at the end (60 % 25 != 0) -> solved
+    (0, dict(max_iter=60), (1, 60)),
+    (1, dict(max_iter=160, eps_abs=1e-5, eps_rel=1e-5), (-3, 160)),   # exact check at the end -> certificate
+    (1, dict(max_iter=310, eps_abs=1e-5, eps_rel=1e-5), (3, 310)),    # approximate check -> primal infeasible inaccurate
+])
+def test_qp_final_checks_after_max_iter(orc, precision, settings, expect):
+    """osqp.c after the main loop: when the last iteration was not a check iteration OSQP first runs a NORMAL termination
+    check (so a QP that converges between the last periodic check and max_iter is `solved`, not `solved inaccurate`), then
+    the approximate one, which can also return the inaccurate infeasibility statuses 3 / 4 (no solution: NaN, and the
+    MPC falls back to its previous plan).  All 76 golden QPs; `expect` = a (status, iterations) pair that must occur."""
+    import torch
+    import mpc_b200
+    TF, C1 = load_golden("teacher_forced.npz"), load_golden("c1_lap.npz")
+    Pd, q, Ax, l, u = (np.concatenate([TF["qp_" + k], C1["qp_" + k]]) for k in ("Pd", "q", "Ax", "l", "u"))
+    B, n = Pd.shape[0], 153
+    Ap, Ai = fixed_pattern(30)
+    xo, ito, sto = orc.batch_qp_solve(30, Pd, q, Ap, Ai, Ax, l, u, **settings)
+    assert ((sto == expect[0]) & (ito == expect[1])).any(), "the fixture no longer reaches the path under test"
+    eng = mpc_b200.Engine(precision=precision, **settings)
+    x = torch.zeros((B, n), dtype=torch.float64, device=_dev())
+    it = torch.zeros(B, dtype=torch.int32, device=_dev())
+    st = torch.zeros(B, dtype=torch.int32, device=_dev())
+    eng.solve_qp(_t(Pd), _t(q), _t(Ax), _t(l), _t(u), x, it, st)
+    eng.sync()
+    x, it, st = x.cpu().numpy(), it.cpu().numpy(), st.cpu().numpy()
+    eng.close()
+    assert np.array_equal(st, sto), list(zip(st[st != sto], sto[st != sto]))
+    assert np.array_equal(it, ito)
+    none = np.isin(sto, (-3, -4, -7, 3, 4))
+    assert np.isnan(x[none]).all() and np.isnan(xo[none]).all() and np.isfinite(x[~none]).all()
+    assert np.abs(x[~none] - xo[~none]).max() <= (1e-6 if precision == 1 else 2 * QP_TOL)
 
 
 def _start_states(track, sc):

@@ -194,6 +194,34 @@ def test_null_direction_is_the_only_one(orc):
     assert (sv < 1e-10).sum() == 1
 
 
+def test_h1_projection_helper_matches_the_svd_null_vector(orc):
+    """tests/conftest.py::h1_null_direction (read off the constraint values) against the SVD null vector of [P; Aeq]."""
+    from conftest import h1_null_direction
+    TF = load_golden("teacher_forced.npz")
+    Ap, Ai = fixed_pattern(30)
+    d = h1_null_direction(30, TF["qp_Pd"][:6], TF["qp_Ax"][:6])
+    for b in range(6):
+        A = sparse.csc_matrix((TF["qp_Ax"][b], Ai, Ap), shape=(246, 153)).toarray()
+        _, sv, vt = np.linalg.svd(np.vstack([np.diag(TF["qp_Pd"][b]), A[:93]]))
+        assert sv[-1] < 1e-10 and abs(abs(vt[-1] @ d[b]) - 1.0) < 1e-12
+
+
+def test_osqp_final_checks_after_max_iter(orc):
+    """osqp.c after the main loop: a NORMAL termination check when the last iteration was not a check iteration, then the
+    approximate one (statuses 2 / 3 / 4).  max_iter = 60 (60 % 25 != 0): QPs converging between iteration 50 and 60 are
+    `solved` (1) at 60 iterations, the rest `solved inaccurate` (2); eps 1e-5 with max_iter 160 / 310 reaches the exact
+    certificate at the final check (-3 at 160) and the inaccurate one (3), both without a solution."""
+    TF, C1 = load_golden("teacher_forced.npz"), load_golden("c1_lap.npz")
+    Pd, q, Ax, l, u = (np.concatenate([TF["qp_" + k], C1["qp_" + k]]) for k in ("Pd", "q", "Ax", "l", "u"))
+    Ap, Ai = fixed_pattern(30)
+    x, it, st = orc.batch_qp_solve(30, Pd, q, Ap, Ai, Ax, l, u, max_iter=60)
+    assert ((st == 1) & (it == 60)).sum() >= 3 and ((st == 2) & (it == 60)).sum() >= 30 and ((st == 1) & (it <= 50)).any()
+    x, it, st = orc.batch_qp_solve(30, Pd, q, Ap, Ai, Ax, l, u, max_iter=160, eps_abs=1e-5, eps_rel=1e-5)
+    assert ((st == -3) & (it == 160)).any()
+    x, it, st = orc.batch_qp_solve(30, Pd, q, Ap, Ai, Ax, l, u, max_iter=310, eps_abs=1e-5, eps_rel=1e-5)
+    assert ((st == 3) & (it == 310)).any() and np.isnan(x[st == 3]).all() and np.isfinite(x[st == -2]).all()
+
+
 def test_full_step_matches_reference_lap(orc, track, orc_path):
     """orc_mpc_step (the C restatement of get_control + drive) against the reference's own closed loop."""
     C1 = load_golden("c1_lap.npz")
