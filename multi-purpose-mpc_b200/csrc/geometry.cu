@@ -635,6 +635,63 @@ raycast_kernel(RaycastArgs a) {
     }
 }
 
+// K4a + width-table replay.  With ONE grid shared by every scenario, update_path_constraints(wp_id, N, ...) is a pure
+// function of the waypoint index (rp.py:522-648 reads the path, the grid and wp_id -- never the car's pose), so the engine
+// ray-casts each of the n_wp horizons once per (path, grid, N, car width) with raycast_kernel itself (mpc_engine's
+// width table) and a closed-loop step only localises the car and copies the row of its waypoint: bit-identical output,
+// 200 distinct ray-casts instead of one per car per step.  Same launch shape as raycast_kernel: one warp per scenario,
+// plus the planner CTA.  Per-scenario grids (obstacle scenarios) never take this path.
+__global__ void __launch_bounds__(256)
+localize_gather_kernel(RaycastArgs a, const double* __restrict__ memo_ub, const double* __restrict__ memo_lb,
+                       const int* __restrict__ memo_flags) {
+    const PathView& pv = a.pv;
+    const int N = a.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int ray_ctas = a.order_out ? (int)gridDim.x - 1 : (int)gridDim.x;
+    if ((int)blockIdx.x == ray_ctas) {
+        plan_solve_order(a.prev_iters, a.flags, a.order_out, a.long_out, a.bucket_of, a.B);
+        return;
+    }
+    for (int b = blockIdx.x * nwarps + warp; b < a.B; b += ray_ctas * nwarps) {
+        const int fl = a.flags ? a.flags[b] : 0;
+        if (fl & (MPC_ST_DEAD | MPC_ST_FINISHED)) continue;
+        int w;
+        if (a.state) {
+            w = localize_warp(a.state, a.spatial_out, pv, a.length, b, a.B, lane);
+            if (w < 0) {
+                if (lane == 0 && a.flags) atomicOr(&a.flags[b], MPC_ST_FINISHED);
+                continue;
+            }
+            if (lane == 0) a.wp_id_out[b] = w;
+        } else {
+            w = a.wp_id[b];
+        }
+        const int st = memo_flags[w];  // what the ray-cast of this horizon reported (incl. MPC_ST_DEAD), 0 = fine
+        if (st) {
+            if (lane == 0 && a.flags) atomicOr(&a.flags[b], st);
+            continue;
+        }
+        for (int n = lane; n < N; n += 32) {
+            a.ub_out[(size_t)b * N + n] = memo_ub[(size_t)w * N + n];
+            a.lb_out[(size_t)b * N + n] = memo_lb[(size_t)w * N + n];
+        }
+    }
+}
+
+void launch_localize_gather(const PathView& pv, const double* memo_ub, const double* memo_lb, const int* memo_flags,
+                            const int* wp_id, int N, double* ub, double* lb, int* flags, int B, cudaStream_t st,
+                            const double* state, int* wp_id_out, double* spatial_out, double length, const int* prev_iters,
+                            int* order_out, int* long_out, unsigned char* bucket_of) {
+    NvtxRange nvtx_("mpc:K4a+K3 localize + width-table replay");
+    RaycastArgs a{};
+    a.prev_iters = prev_iters; a.order_out = (order_out && bucket_of) ? order_out : nullptr; a.long_out = long_out; a.bucket_of = bucket_of;
+    a.state = state; a.wp_id_out = wp_id_out; a.spatial_out = spatial_out; a.length = length;
+    a.pv = pv; a.wp_id = wp_id; a.first_offset = 1; a.N = N; a.ub_out = ub; a.lb_out = lb; a.flags = flags; a.B = B;
+    const int warps = 8;
+    const int need_ctas = (B + warps - 1) / warps, max_ctas = sm_count() * 8;
+    const int grid = (need_ctas < max_ctas ? need_ctas : max_ctas) + (a.order_out ? 1 : 0);
+    localize_gather_kernel<<<grid, warps * 32, 0, st>>>(a, memo_ub, memo_lb, memo_flags);
+}
+
 static size_t raycast_scratch_bytes(int N) {
     return (size_t)N * kMaxSeg * sizeof(short4) + (size_t)N * 4 * sizeof(double) + (size_t)((N + 3) & ~3) * sizeof(int);
 }
