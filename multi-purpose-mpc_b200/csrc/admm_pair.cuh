@@ -222,6 +222,21 @@ __device__ __forceinline__ void ruiz_scale2(const GroupComm<LPS>& cm, Stage2& s,
 #ifndef MPC_COMPENSATED_V
 #define MPC_COMPENSATED_V 1
 #endif
+// y-form (A/B switch, OFF): the duals are state -- y_d of the dynamics rows is accumulated (y_d += dy_d), y_b of a bound row is
+// rho (v - z) by construction -- and the right-hand side is  P x + q + A'(y + rho r)  with ONE A' product per pass, instead of
+// tracking u = q + A'y through a second product u += A'dy.  Measured on the GPU (round 2): on QPs that OSQP solves it is
+// 3.5x closer to the fp64 oracle (4096 random QPs, identical traces: max |x - oracle| 7.7e-4 -> 2.2e-4; 76 golden: 3.5e-4 ->
+// 1.4e-4), but it is NOT faster (the second product sits off the dependent chain: 116.9 vs 117.7 us) and it degrades on
+// primal-infeasible QPs: there y grows without bound while A'y stays bounded, so A'y computed from y loses what u, fed by the
+// vanishing increments A'dy, keeps -- certificates come a check apart 8x more often (0.07 % -> 0.76 % of the QPs) and one
+// infeasible QP in 741 is never certified (status 2 instead of -3, i.e. the controller would apply an iterate where the
+// reference replays its previous plan).  The status is what the reference reacts to, so the u-form stays.
+#ifndef MPC_Y_FORM
+#define MPC_Y_FORM 0
+#endif
+#ifndef MPC_PASS_Q_REG
+#define MPC_PASS_Q_REG 0
+#endif
 template <int LPS> struct PcrCoef {  // float4 per lane
     static constexpr int kF4 = (9 * ((LPS == 32 ? 5 : (LPS == 16 ? 4 : (LPS == 8 ? 3 : 2))) - 1) + 1) / 2;
 };
@@ -571,12 +586,12 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
     sm[54 * LPS + gl] = mk(cm.max(nq_s), cm.max(nq_u));
     sm[55 * LPS + gl] = mk(s.cs, 1.0f / s.cs);
     const f2 zero = bc(0.0f);
-    f2 x[5], u[5], vb[5], zb[5], rbd[5], rdy[3];
+    f2 x[5], u[5], yd[3], vb[5], zb[5], rbd[5], rdy[3];   // u: u-form only; yd: y-form only
     f2 vl4 = zero, zl4 = zero;  // low words of v and z of the curvature row (MPC_COMPENSATED_V)
 #pragma unroll
     for (int i = 0; i < 5; ++i) { x[i] = zero; u[i] = s.q[i]; vb[i] = zero; zb[i] = zero; rbd[i] = zero; }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) rdy[i] = zero;
+    for (int i = 0; i < 3; ++i) { rdy[i] = zero; yd[i] = zero; }
     f2 rd = bc(rdf);
     bool done = !live;
     int iter = 0;
@@ -598,13 +613,21 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
     auto pass = [&](const bool first) __attribute__((always_inline)) {
         f2 td[3], tb[5], rhs[5], s1d[3], s1b[5];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) td[i] = pmul(rd, rdy[i]);
+        for (int i = 0; i < 3; ++i) td[i] = MPC_Y_FORM ? pfma(rd, rdy[i], yd[i]) : pmul(rd, rdy[i]);
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            rhs[i] = pfma(MPC_PASS_P_REG ? s.P[i] : ldsv(&sm[(49 + i) * LPS + gl]), x[i], u[i]);
-            if (!(LOOSE && (i == 1 || i == 2))) tb[i] = pmul(rb[i], rbd[i]);
+            const f2 lin = MPC_Y_FORM ? (MPC_PASS_Q_REG ? s.q[i] : ldsv(&sm[(29 + i) * LPS + gl])) : u[i];
+            rhs[i] = pfma(MPC_PASS_P_REG ? s.P[i] : ldsv(&sm[(49 + i) * LPS + gl]), x[i], lin);
+            if (LOOSE && (i == 1 || i == 2)) continue;
+            if (MPC_Y_FORM) {  // y + rho r = rho ((v - z) + r)
+                f2 vz = psub(vb[i], zb[i]);
+                if (MPC_COMPENSATED_V && i == 4) vz = padd(vz, psub(vl4, zl4));
+                tb[i] = pmul(rb[i], padd(vz, rbd[i]));
+            } else {
+                tb[i] = pmul(rb[i], rbd[i]);
+            }
         }
-        At_apply2<LPS, LOOSE>(cm, s, td, tb, rhs, rhs);  // rhs = P x + u + A'(rho r);  S D = -rhs
+        At_apply2<LPS, LOOSE>(cm, s, td, tb, rhs, rhs);  // rhs = P x + q + A'(y + rho r);  S D = -rhs
         kkt_solve2<LPS>(cm, f, rhs, dl, cf);
 #pragma unroll
         for (int i = 0; i < 5; ++i) { dl[i] = pmul(dl[i], nal2); x[i] = padd(x[i], dl[i]); }  // dl = alpha D
@@ -649,7 +672,12 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
                 ed[i] = psub(ed[i], pmul(rd, dd));
             }
         }
-        At_apply2<LPS, LOOSE>(cm, s, ed, eb, u, u);
+        if (MPC_Y_FORM) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) yd[i] = padd(yd[i], ed[i]);
+        } else {
+            At_apply2<LPS, LOOSE>(cm, s, ed, eb, u, u);
+        }
     };
     // termination check / rho adaptation after a pass; returns true when every scenario of the warp is done
     // phase 0 = iterating.  After max_iter passes OSQP (osqp.c, after its main loop) runs a NORMAL termination check if the
@@ -692,11 +720,25 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
             }
             float du_s = 0, du_u = 0, npx_s = 0, npx_u = 0, naty_s = 0, naty_u = 0;
             const float nq_s = ldsv(&sm[54 * LPS + gl]).x, nq_u = ldsv(&sm[54 * LPS + gl]).y, cs = ldsv(&sm[55 * LPS + gl]).x, cinv = ldsv(&sm[55 * LPS + gl]).y;
+            f2 aty5[5];
+            if (MPC_Y_FORM) {  // A'y from the duals themselves: y_b = rho (v - z)
+                f2 yb5[5];
+                const f2 z5[5] = {zero, zero, zero, zero, zero};
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    if (LOOSE && (i == 1 || i == 2)) { yb5[i] = zero; continue; }
+                    f2 vz = psub(vb[i], zb[i]);
+                    if (MPC_COMPENSATED_V && i == 4) vz = padd(vz, psub(vl4, zl4));
+                    yb5[i] = pmul(rb[i], vz);
+                }
+                At_apply2<LPS, LOOSE>(cm, s, yd, yb5, z5, aty5);
+            }
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
                 const f2 px = pmul(ldsv(&sm[(49 + i) * LPS + gl]), x[i]);
-                const f2 r = padd(px, u[i]);
-                const f2 aty = psub(u[i], ldsv(&sm[(29 + i) * LPS + gl]));
+                const f2 qi = ldsv(&sm[(29 + i) * LPS + gl]);
+                const f2 r = MPC_Y_FORM ? padd(padd(px, qi), aty5[i]) : padd(px, u[i]);
+                const f2 aty = MPC_Y_FORM ? aty5[i] : psub(u[i], qi);
                 amax(du_s, r); amax(du_u, pmul(r, Di[i]));
                 amax(npx_s, px); amax(npx_u, pmul(px, Di[i]));
                 amax(naty_s, aty); amax(naty_u, pmul(aty, Di[i]));

@@ -100,6 +100,12 @@ struct mpc_engine {
     // profiling
     int profiling = 0;
     int no_solve_order = 0;  // MPC_SOLVE_ORDER=off: scenarios are solved in index order (A/B switch)
+    // width table (shared grid only): update_path_constraints of every waypoint's horizon, ray-cast once per
+    // (path, border cells, grid, N, car width) -- see geometry.cu::localize_gather_kernel
+    DevBuf<double> memo_ub, memo_lb;   // [n_wp][N]
+    DevBuf<int> memo_flags, memo_wp;   // [n_wp]
+    bool memo_valid = false;
+    int no_memo = 0;                   // MPC_WIDTH_MEMO=off: ray-cast per car per step (A/B switch, bench.py reports both)
     double prof_ms[4] = {0, 0, 0, 0};
     int64_t prof_launches[4] = {0, 0, 0, 0};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -122,6 +128,7 @@ static void refresh_params(mpc_engine* h) {
 }
 
 static void drop_graph(mpc_engine* h) {
+    h->memo_valid = false;  // every caller changes something the width table depends on (or B: rebuilt lazily, cheap)
     for (int i = 0; i < 2; ++i) {
         if (h->graph_exec[i]) cudaGraphExecDestroy(h->graph_exec[i]);
         h->graph_exec[i] = nullptr;
@@ -184,6 +191,8 @@ int mpc_engine_create(const mpc_config* cfg, mpc_engine** out) {
     {
         const char* e2 = getenv("MPC_SOLVE_ORDER");
         h->no_solve_order = (e2 && e2[0] == 'o' && e2[1] == 'f') ? 1 : 0;
+        const char* e3 = getenv("MPC_WIDTH_MEMO");
+        h->no_memo = (e3 && e3[0] == 'o' && e3[1] == 'f') ? 1 : 0;
     }
     cudaMemset(h->d_err.p, 0, sizeof(int));
     for (int i = 0; i < 5; ++i)
@@ -600,6 +609,34 @@ static bool prefer_stage_kernel(const mpc_engine* h) {
     return (long)nl * 50 > (long)h->B;
 }
 
+// Builds the width table if the closed-loop step can use it (one grid shared by all scenarios).  NOT capturable (it
+// synchronises): the entry points call it before they enqueue or capture a step.
+static int ensure_width_memo(mpc_engine* h) {
+    if (h->grids_B || h->no_memo || h->memo_valid) return 0;
+    if (!h->rowspan_valid) return 0;  // launch_raycast reports the missing tables
+    const int n = h->n_wp, N = h->cfg.N;
+    const double sm = h->cfg.car_width / std::sqrt(2.0);
+    CUDA_OK(h->memo_ub.alloc((size_t)n * N));
+    CUDA_OK(h->memo_lb.alloc((size_t)n * N));
+    CUDA_OK(h->memo_flags.alloc(n));
+    CUDA_OK(h->memo_wp.alloc(n));
+    std::vector<int> iota(n);
+    for (int i = 0; i < n; ++i) iota[i] = i;
+    cudaStream_t s = h->stream;
+    CUDA_OK(cudaMemcpyAsync(h->memo_wp.p, iota.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemsetAsync(h->memo_flags.p, 0, n * sizeof(int), s));
+    CUDA_OK(cudaMemsetAsync(h->memo_ub.p, 0, (size_t)n * N * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(h->memo_lb.p, 0, (size_t)n * N * sizeof(double), s));
+    // virtual scenario w = "a car whose current waypoint is w": exactly the call MPC.get_control makes (MPC.py:116-118)
+    launch_raycast(h->d_base.p, 0, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->d_ray_cells.p, h->d_ray_len.p, h->memo_wp.p, 1, N,
+                   2 * sm, sm, h->memo_ub.p, h->memo_lb.p, nullptr, h->memo_flags.p, n, h->rowspan_valid, s);
+    ++h->launches;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(s));
+    h->memo_valid = true;
+    return 0;
+}
+
 static int enqueue_step(mpc_engine* h, bool with_stats, bool timed, bool stage_hint = false) {
     const int B = h->B;
     cudaStream_t s = h->stream;
@@ -609,9 +646,14 @@ static int enqueue_step(mpc_engine* h, bool with_stats, bool timed, bool stage_h
     if (!timed) {
         // the solve order is planned by one extra CTA of the raycast launch from the previous step's iteration counts
         int* order = (h->cfg.precision == 0 && B <= (1 << 16) && !h->no_solve_order) ? h->s_order.p : nullptr;
-        launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->d_ray_cells.p, h->d_ray_len.p, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm,
-                       h->s_ub.p, h->s_lb.p, nullptr, h->s_flags.p, B, h->rowspan_valid, s, h->s_state.p, h->s_wp_id.p,
-                       h->s_spatial.p, h->length, h->s_iters.p, order, order ? h->d_long : nullptr, h->s_bucket.p);
+        if (h->memo_valid && !h->grids_B)
+            launch_localize_gather(h->pv, h->memo_ub.p, h->memo_lb.p, h->memo_flags.p, h->s_wp_id.p, h->cfg.N, h->s_ub.p, h->s_lb.p,
+                                   h->s_flags.p, B, s, h->s_state.p, h->s_wp_id.p, h->s_spatial.p, h->length, h->s_iters.p, order,
+                                   order ? h->d_long : nullptr, h->s_bucket.p);
+        else
+            launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->d_ray_cells.p, h->d_ray_len.p, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm,
+                           h->s_ub.p, h->s_lb.p, nullptr, h->s_flags.p, B, h->rowspan_valid, s, h->s_state.p, h->s_wp_id.p,
+                           h->s_spatial.p, h->length, h->s_iters.p, order, order ? h->d_long : nullptr, h->s_bucket.p);
         int r = launch_assemble_solve(h->cfg.precision, h->mp, h->st, h->pv, h->s_spatial.p, h->s_wp_id.p, h->s_control.p,
                                       h->s_ub.p, h->s_lb.p, h->s_infeas.p, h->s_u.p, nullptr, h->s_iters.p,
                                       h->s_qp_status.p, h->s_flags.p, B, s, h->s_state.p, h->cfg.Ts, order, stage_hint);
@@ -625,8 +667,12 @@ static int enqueue_step(mpc_engine* h, bool with_stats, bool timed, bool stage_h
     cudaEventRecord(h->ev[0], s);
     launch_localize(h->s_state.p, h->s_wp_id.p, h->s_spatial.p, h->s_flags.p, h->pv, h->length, B, s);
     cudaEventRecord(h->ev[1], s);
-    launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->d_ray_cells.p, h->d_ray_len.p, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm,
-                   h->s_ub.p, h->s_lb.p, nullptr, h->s_flags.p, B, h->rowspan_valid, s);
+    if (h->memo_valid && !h->grids_B)
+        launch_localize_gather(h->pv, h->memo_ub.p, h->memo_lb.p, h->memo_flags.p, h->s_wp_id.p, h->cfg.N, h->s_ub.p, h->s_lb.p,
+                               h->s_flags.p, B, s);
+    else
+        launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->d_ray_cells.p, h->d_ray_len.p, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm,
+                       h->s_ub.p, h->s_lb.p, nullptr, h->s_flags.p, B, h->rowspan_valid, s);
     cudaEventRecord(h->ev[2], s);
     int r = launch_assemble_solve(h->cfg.precision, h->mp, h->st, h->pv, h->s_spatial.p, h->s_wp_id.p, h->s_control.p,
                                   h->s_ub.p, h->s_lb.p, h->s_infeas.p, h->s_u.p, nullptr, h->s_iters.p,
@@ -645,12 +691,14 @@ static int enqueue_step(mpc_engine* h, bool with_stats, bool timed, bool stage_h
 int mpc_step(mpc_engine* h) {
     if (!h || h->B <= 0) return fail(MPC_E_STATE, "mpc_scenarios_init first");
     if (int r = need(h, true, true)) return r;
+    if (int r = ensure_width_memo(h)) return r;
     return enqueue_step(h, false, false, prefer_stage_kernel(h));
 }
 
 static int ensure_graph(mpc_engine* h) {
     if (h->graph_exec[0] && h->graph_exec[1] && h->graph_B == h->B) return 0;
     drop_graph(h);
+    if (int r0 = ensure_width_memo(h)) return r0;  // before the capture: it synchronises
     cudaStream_t cap = h->stream;
     cudaStream_t own = nullptr;
     if (cap == nullptr) {  // the legacy default stream cannot be captured
@@ -714,6 +762,7 @@ int mpc_run_closed_loop(mpc_engine* h, int32_t max_steps, double* h_stats) {
     if (int r = need(h, true, true)) return r;
     if (max_steps < 0) return fail(MPC_E_INVALID, "max_steps < 0");
     if (h->profiling) {
+        if (int r = ensure_width_memo(h)) return r;
         for (int k = 0; k < max_steps; ++k) {
             if (int r = enqueue_step(h, true, true)) return r;
             CUDA_OK(cudaEventSynchronize(h->ev[4]));
@@ -790,6 +839,7 @@ static int ensure_io_graph(mpc_engine* h, double* h_state, double* h_u_out, int3
         h->io_graph[i] = nullptr;
     }
     const size_t B = h->B;
+    if (int r0 = ensure_width_memo(h)) return r0;  // before the capture: it synchronises
     cudaStream_t cap = h->stream, own = nullptr;
     if (cap == nullptr) {
         CUDA_OK(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
@@ -851,6 +901,7 @@ int mpc_step_host(mpc_engine* h, double* h_state, double* h_u_out, int32_t* h_fl
     }
     // pageable caller buffers: staged through the engine's pinned block
     if (int r = ensure_pinned_io(h)) return r;
+    if (int r = ensure_width_memo(h)) return r;
     const size_t io_bytes = 6 * B * sizeof(double) + B * sizeof(int);
     memcpy(h->pin_state, h_state, 4 * B * sizeof(double));
     CUDA_OK(cudaMemcpyAsync(h->s_state.p, h->pin_state, 4 * B * sizeof(double), cudaMemcpyHostToDevice, s));

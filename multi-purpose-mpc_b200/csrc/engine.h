@@ -28,6 +28,11 @@ void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridV
                     cudaStream_t st, const double* state = nullptr, int* wp_id_out = nullptr,
                     double* spatial_out = nullptr, double length = 0.0, const int* prev_iters = nullptr,
                     int* order_out = nullptr, int* long_out = nullptr, unsigned char* bucket_of = nullptr);
+void launch_localize_gather(const PathView& pv, const double* memo_ub, const double* memo_lb, const int* memo_flags,
+                            const int* wp_id, int N, double* ub, double* lb, int* flags, int B, cudaStream_t st,
+                            const double* state = nullptr, int* wp_id_out = nullptr, double* spatial_out = nullptr,
+                            double length = 0.0, const int* prev_iters = nullptr, int* order_out = nullptr,
+                            int* long_out = nullptr, unsigned char* bucket_of = nullptr);
 void launch_localize(const double* state, int* wp_id, double* spatial, int* flags, const PathView& pv, double length,
                      int B, cudaStream_t st);
 void launch_rollout(double* state, const double* spatial, const int* wp_id, const double* u, const int* flags,

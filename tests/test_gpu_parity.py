@@ -507,7 +507,7 @@ for k in range(12):
     o = eng.scenarios_read()
     iters.append(o["iters"].copy()); stats.append(o["qp_status"].copy())
 np.savez(os.environ["MPC_OUT"], state=o["state"], u=o["u"], control=o["control"], flags=o["flags"], iters=np.array(iters),
-         qp_status=np.array(stats))
+         qp_status=np.array(stats), ub=o["ub"], lb=o["lb"], wp_id=o["wp_id"])
 eng.close()
 """
 
@@ -529,12 +529,18 @@ def test_solve_order_and_kernel_variant_do_not_change_the_answers(tmp_path):
     (a) planning the solve order from the previous step's iteration counts (which changes which scenarios share a
         warp) must not change a single bit -- a scenario's arithmetic never depends on its warp-mates;
     (b) the paired-stage and the lane-per-stage fp32 kernels are different roundings of the same OSQP iteration:
-        identical iteration counts where OSQP solves, controls within the fp32 tolerance."""
+        identical iteration counts where OSQP solves, controls within the fp32 tolerance;
+    (c) replaying the engine's width table (shared grid: update_path_constraints is a function of the waypoint only) gives
+        the same bits as ray-casting for every car in every step."""
     # MPC_ADMM_KERNEL pins the solve kernel (by default the engine switches per step on the planner's long-solve count)
     a = _run_variant(tmp_path, "pair_ordered", MPC_ADMM_KERNEL="pair")
     b = _run_variant(tmp_path, "pair_unordered", MPC_ADMM_KERNEL="pair", MPC_SOLVE_ORDER="off")
     for k in ("state", "u", "control", "flags", "iters", "qp_status"):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
+    # (c) the width table (one ray-cast per waypoint horizon, replayed per car) against ray-casting per car per step
+    m = _run_variant(tmp_path, "pair_no_width_table", MPC_ADMM_KERNEL="pair", MPC_WIDTH_MEMO="off")
+    for k in ("state", "u", "control", "flags", "iters", "qp_status", "ub", "lb", "wp_id"):
+        assert np.array_equal(a[k], m[k], equal_nan=True), k
     c = _run_variant(tmp_path, "stage", MPC_ADMM_KERNEL="stage")
     assert np.array_equal(a["flags"], c["flags"]) and np.array_equal(a["qp_status"], c["qp_status"])
     solved = a["qp_status"] == 1
