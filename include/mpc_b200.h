@@ -132,6 +132,18 @@ int mpc_get_grid(mpc_engine *h, int32_t b, int8_t *h_data_out);
  * Synchronous. */
 int mpc_compute_width(mpc_engine *h, double max_width, double *h_ub, double *h_lb, double *h_border);
 
+/* ReferencePath._compute_width / _get_min_width for T tracks in one launch (reference_path.py:206-287; SURVEY 8f-2: scenarios
+ * that randomise the TRACK, not only the obstacles).  Track t has its own base map h_maps[t] (H x W int8, 1 free / 0 occupied,
+ * row = world-y cell, as Map.data) and its own waypoints: h_tables[t] is the double[12][n_wp_max] table mpc_set_path takes,
+ * of which the first h_n_wp[t] columns are valid.  All maps share H, W, origin and resolution.
+ * Outputs (host, any may be NULL): h_ub / h_lb [T][n_wp_max] = Waypoint.ub / .lb, h_border [T][n_wp_max][4] = the static
+ * border cells (ub_x, ub_y, lb_x, lb_y), h_err [T] = MPC_ST_INDEX_ERROR where a ray left the map (the reference raises
+ * IndexError, reference_path.py:279).  Does not touch the engine's own path / grid. */
+int mpc_compute_width_batch(mpc_engine *h, int32_t T, const int8_t *h_maps, int32_t H, int32_t W, double origin_x,
+                            double origin_y, double resolution, const double *h_tables, const int32_t *h_n_wp,
+                            int32_t n_wp_max, double max_width, double *h_ub, double *h_lb, double *h_border,
+                            int32_t *h_err);
+
 /* ---- K4 front: get_current_waypoint + t2s (sbm.py:256-279, 183-219) ------------------------- */
 int mpc_localize_t2s(mpc_engine *h, const double *d_state, int32_t *d_wp_id, double *d_spatial,
                      int32_t *d_flags, int32_t B);

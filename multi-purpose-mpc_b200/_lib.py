@@ -37,7 +37,7 @@ class MpcConfig(C.Structure):
 EXPORTS = [
     "mpc_config_default", "mpc_last_error", "mpc_abi_version", "mpc_engine_create", "mpc_engine_destroy",
     "mpc_engine_set_stream", "mpc_engine_update_config", "mpc_engine_sync", "mpc_set_path", "mpc_set_vref",
-    "mpc_set_base_grid", "mpc_set_obstacles", "mpc_get_grid", "mpc_compute_width", "mpc_localize_t2s",
+    "mpc_set_base_grid", "mpc_set_obstacles", "mpc_get_grid", "mpc_compute_width", "mpc_compute_width_batch", "mpc_localize_t2s",
     "mpc_raycast", "mpc_update_path_constraints", "mpc_assemble_solve", "mpc_solve_qp", "mpc_rollout",
     "mpc_scenarios_init", "mpc_scenarios_set_state", "mpc_step", "mpc_run_closed_loop", "mpc_step_host",
     "mpc_scenarios_ptrs", "mpc_scenarios_read", "mpc_launch_count", "mpc_set_profiling", "mpc_get_profile",
@@ -76,6 +76,9 @@ def load():
     L.mpc_set_obstacles.argtypes = [vp, c_double_p, c_int_p, C.c_int32]
     L.mpc_get_grid.argtypes = [vp, C.c_int32, c_i8_p]
     L.mpc_compute_width.argtypes = [vp, C.c_double, c_double_p, c_double_p, c_double_p]
+    L.mpc_compute_width_batch.argtypes = [vp, C.c_int32, C.POINTER(C.c_int8), C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                          C.c_double, c_double_p, c_int_p, C.c_int32, C.c_double, c_double_p, c_double_p,
+                                          c_double_p, c_int_p]
     L.mpc_localize_t2s.argtypes = [vp, vp, vp, vp, vp, C.c_int32]
     L.mpc_raycast.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int32]
     L.mpc_update_path_constraints.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_double, C.c_double, vp, vp, vp,
@@ -240,6 +243,25 @@ class Engine:
         ub, lb, border = np.empty(self.n_wp), np.empty(self.n_wp), np.empty((self.n_wp, 4))
         _check(self.L.mpc_compute_width(self.h, float(max_width), _dp(ub), _dp(lb), _dp(border)))
         return ub, lb, border
+
+    def compute_width_batch(self, maps, origin, resolution, tables, max_width):
+        """ReferencePath._compute_width for T tracks at once.  maps: [T, H, W] int8 (Map.data of every track), tables: list
+        of T double[12][n_wp_t] path tables (path_table()).  Returns (ub, lb, border, err): [T, n_max], [T, n_max],
+        [T, n_max, 4], [T]; columns beyond a track's own n_wp are zero."""
+        maps = np.ascontiguousarray(maps, dtype=np.int8)
+        T, H, W = maps.shape
+        assert len(tables) == T
+        n_wp = np.array([t.shape[1] for t in tables], dtype=np.int32)
+        n_max = int(n_wp.max())
+        tab = np.zeros((T, 12, n_max))
+        for t, a in enumerate(tables):
+            tab[t, :, :a.shape[1]] = a
+        ub, lb, border = np.empty((T, n_max)), np.empty((T, n_max)), np.empty((T, n_max, 4))
+        err = np.zeros(T, np.int32)
+        _check(self.L.mpc_compute_width_batch(self.h, T, maps.ctypes.data_as(c_i8_p), H, W, float(origin[0]), float(origin[1]),
+                                              float(resolution), _dp(tab), _ip(n_wp), n_max, float(max_width), _dp(ub), _dp(lb),
+                                              _dp(border), _ip(err)))
+        return ub, lb, border, err
 
     # ---- per-step kernels on caller-owned torch CUDA tensors ------------------------------------
     def localize_t2s(self, state, wp_id, spatial, flags=None):

@@ -450,6 +450,71 @@ int mpc_compute_width(mpc_engine* h, double max_width, double* h_ub, double* h_l
     return compute_rowspan(h);
 }
 
+// ReferencePath._compute_width for T tracks in one launch (rp.py:206-287; SURVEY 8f-2: per-scenario BASE maps).  Stateless
+// with respect to the engine: nothing of it changes the path / grid the engine steps on.
+int mpc_compute_width_batch(mpc_engine* h, int32_t T, const int8_t* h_maps, int32_t H, int32_t W, double ox, double oy,
+                            double res, const double* h_tables, const int32_t* h_n_wp, int32_t n_wp_max, double max_width,
+                            double* h_ub, double* h_lb, double* h_border, int32_t* h_err) {
+    if (!h) return fail(MPC_E_INVALID, "null engine");
+    if (T <= 0) return 0;
+    if (!h_maps || !h_tables || !h_n_wp || H <= 0 || W <= 0 || n_wp_max <= 0 || !(res > 0))
+        return fail(MPC_E_INVALID, "bad arguments to mpc_compute_width_batch");
+    for (int t = 0; t < T; ++t)
+        if (h_n_wp[t] < 0 || h_n_wp[t] > n_wp_max) return fail(MPC_E_INVALID, "n_wp[t] outside [0, n_wp_max]");
+    GridView g;
+    g.H = H; g.W = W; g.ox = ox; g.oy = oy; g.res = res;
+    g.pitch_words = ((W + 511) / 512) * 16;  // rows padded to 64 bytes, as mpc_set_base_grid does
+    const size_t words = (size_t)H * g.pitch_words;
+    std::vector<uint32_t> bits(words * (size_t)T, 0u);
+    for (int t = 0; t < T; ++t) {
+        const int8_t* data = h_maps + (size_t)t * H * W;
+        uint32_t* b = bits.data() + (size_t)t * words;
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x)
+                if (data[(size_t)y * W + x] == 1) b[(size_t)y * g.pitch_words + (x >> 5)] |= 1u << (x & 31);
+    }
+    DevBuf<uint32_t> d_bits;
+    DevBuf<double> d_tab, d_ub, d_lb, d_border;
+    DevBuf<int> d_n, d_err;
+    struct Release {  // DevBuf has no destructor (engine members are released explicitly): free the temporaries on every path
+        DevBuf<uint32_t>& a; DevBuf<double>&b, &c, &d, &e; DevBuf<int>&f, &g;
+        ~Release() { a.release(); b.release(); c.release(); d.release(); e.release(); f.release(); g.release(); }
+    } release_{d_bits, d_tab, d_ub, d_lb, d_border, d_n, d_err};
+    cudaStream_t s = h->stream;
+    const size_t nt = (size_t)T * n_wp_max;
+    CUDA_OK(d_bits.alloc(bits.size()));
+    CUDA_OK(d_tab.alloc(12 * nt));
+    CUDA_OK(d_ub.alloc(nt));
+    CUDA_OK(d_lb.alloc(nt));
+    CUDA_OK(d_border.alloc(4 * nt));
+    CUDA_OK(d_n.alloc(T));
+    CUDA_OK(d_err.alloc(T));
+    CUDA_OK(cudaMemcpyAsync(d_bits.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(d_tab.p, h_tables, 12 * nt * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(d_n.p, h_n_wp, T * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemsetAsync(d_err.p, 0, T * sizeof(int), s));
+    CUDA_OK(cudaMemsetAsync(d_ub.p, 0, nt * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(d_lb.p, 0, nt * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(d_border.p, 0, 4 * nt * sizeof(double), s));
+    launch_compute_width_batch(d_bits.p, words, g, d_tab.p, n_wp_max, d_n.p, T, max_width, d_ub.p, d_lb.p, d_border.p, d_err.p, s);
+    ++h->launches;
+    CUDA_OK(cudaGetLastError());
+    std::vector<int> err(T, 0);
+    if (h_ub) CUDA_OK(cudaMemcpyAsync(h_ub, d_ub.p, nt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (h_lb) CUDA_OK(cudaMemcpyAsync(h_lb, d_lb.p, nt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (h_border) CUDA_OK(cudaMemcpyAsync(h_border, d_border.p, 4 * nt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(err.data(), d_err.p, T * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    int any = 0;
+    for (int t = 0; t < T; ++t) {
+        if (h_err) h_err[t] = err[t];
+        any |= err[t];
+    }
+    // the reference raises IndexError for a ray that leaves the map (rp.py:279); per-track flags say which
+    if (any && !h_err) return fail(MPC_E_INVALID, "a width ray left the map on at least one track (pass h_err to learn which)");
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 static int need(mpc_engine* h, bool grid, bool border) {
     if (!h) return fail(MPC_E_INVALID, "null engine");

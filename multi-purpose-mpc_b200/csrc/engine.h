@@ -18,6 +18,9 @@ void launch_rasterize(const uint32_t* base, uint32_t* grids, int words, const Gr
                       const int* offsets, int B, cudaStream_t st);
 void launch_compute_width(const uint32_t* grid, const GridView& g, const PathView& pv, double max_width, double* ub,
                           double* lb, double* border, int* err, cudaStream_t st);
+void launch_compute_width_batch(const uint32_t* grids, size_t grid_stride_words, const GridView& g, const double* tables,
+                                int n_max, const int* n_wp, int T, double max_width, double* ub, double* lb, double* border,
+                                int* err, cudaStream_t st);
 int raycast_plan(const GridView& g, int N, bool shared_grid, int max_rows, bool rowspan_ok, int* warps, int* stage_rows,
                  size_t* smem, int B = 0);
 void launch_build_ray_table(const GridView& g, const PathView& pv, uint32_t* cells, int* len, int max_len,

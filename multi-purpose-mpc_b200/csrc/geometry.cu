@@ -92,15 +92,26 @@ void launch_rasterize(const uint32_t* base, uint32_t* grids, int words, const Gr
 // K3b: ReferencePath._compute_width / _get_min_width (rp.py:206-287)
 // one warp per (waypoint, side); lanes 0..8 walk the 9 anti-aliased rays (target cell +-1).
 // ------------------------------------------------------------------------------------------------
-__global__ void compute_width_kernel(const uint32_t* __restrict__ grid, GridView g, PathView pv, double max_width,
+// Batched over tracks (blockIdx.y): track t has its own bit grid (grid_stride_words apart) and its own waypoint table
+// (double[12][n_max] rows as mpc_set_path takes them, table_stride doubles apart) with n_wp_arr[t] valid waypoints; the
+// single-track call is T = 1 with the engine's own tables.
+__global__ void compute_width_kernel(const uint32_t* __restrict__ grids, size_t grid_stride_words, GridView g,
+                                     const double* __restrict__ tables, size_t table_stride, int n_max,
+                                     const int* __restrict__ n_wp_arr, int n_wp_single, double max_width,
                                      double* __restrict__ out_ub, double* __restrict__ out_lb,
                                      double* __restrict__ out_border, int* __restrict__ err_flag) {
+    const int t = blockIdx.y;
+    const int n_wp = n_wp_arr ? n_wp_arr[t] : n_wp_single;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= 2 * pv.n_wp) return;
+    if (warp >= 2 * n_wp) return;
+    const uint32_t* grid = grids + (size_t)t * grid_stride_words;
+    const double* tab = tables + (size_t)t * table_stride;
+    out_ub += (size_t)t * n_max; out_lb += (size_t)t * n_max; out_border += (size_t)t * n_max * 4;
     const int k = warp >> 1, side = warp & 1;
-    const double wx = pv.x[k], wy = pv.y[k];
-    const double ca = side == 0 ? pv.cos_ub[k] : pv.cos_lb[k];  // angle = mod(psi +- pi/2 + pi, 2pi) - pi (rp.py:221-225)
-    const double sa = side == 0 ? pv.sin_ub[k] : pv.sin_lb[k];
+    const double wx = tab[k], wy = tab[(size_t)n_max + k];
+    // angle = mod(psi +- pi/2 + pi, 2pi) - pi (rp.py:221-225): rows 8 / 9 (upper) and 10 / 11 (lower) of the table
+    const double ca = tab[(size_t)(side == 0 ? 8 : 10) * n_max + k];
+    const double sa = tab[(size_t)(side == 0 ? 9 : 11) * n_max + k];
     int tx, ty, px, py;
     w2m(g, wx + max_width * ca, wy + max_width * sa, tx, ty);  // rp.py:227
     w2m(g, wx, wy, px, py);                                    // rp.py:263
@@ -121,7 +132,7 @@ __global__ void compute_width_kernel(const uint32_t* __restrict__ grid, GridView
             return true;
         });
     }
-    if (__any_sync(0xffffffffu, bad)) { if (lane == 0) atomicOr(err_flag, MPC_ST_INDEX_ERROR); }
+    if (__any_sync(0xffffffffu, bad)) { if (lane == 0) atomicOr(&err_flag[t], MPC_ST_INDEX_ERROR); }
     // sequential `<` over paths in order: the smallest distance wins, ties go to the earliest path
     double wbest = best;
     int wl = found ? lane : 64;
@@ -148,7 +159,18 @@ void launch_compute_width(const uint32_t* grid, const GridView& g, const PathVie
                           double* lb, double* border, int* err, cudaStream_t st) {
     NvtxRange nvtx_("mpc:K3b compute_width");
     const int warps = 2 * pv.n_wp;
-    compute_width_kernel<<<(warps * 32 + 127) / 128, 128, 0, st>>>(grid, g, pv, max_width, ub, lb, border, err);
+    // the engine's path rows are contiguous: double[13][n_wp] starting at pv.x (engine.cu::bind_path)
+    compute_width_kernel<<<dim3((warps * 32 + 127) / 128, 1), 128, 0, st>>>(grid, 0, g, pv.x, 0, pv.n_wp, nullptr, pv.n_wp, max_width,
+                                                                         ub, lb, border, err);
+}
+
+void launch_compute_width_batch(const uint32_t* grids, size_t grid_stride_words, const GridView& g, const double* tables,
+                                int n_max, const int* n_wp, int T, double max_width, double* ub, double* lb, double* border,
+                                int* err, cudaStream_t st) {
+    NvtxRange nvtx_("mpc:K3b compute_width (batched over tracks)");
+    const int warps = 2 * n_max;
+    compute_width_kernel<<<dim3((warps * 32 + 127) / 128, T), 128, 0, st>>>(grids, grid_stride_words, g, tables, (size_t)12 * n_max,
+                                                                         n_max, n_wp, 0, max_width, ub, lb, border, err);
 }
 
 // ------------------------------------------------------------------------------------------------

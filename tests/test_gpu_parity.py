@@ -117,6 +117,43 @@ def test_static_width_bit_exact(engine_factory, track, orc, orc_path):
     assert ulps(ub, track.wp_ub).max() <= 1 and ulps(lb, track.wp_lb).max() <= 1                       # widths vs libm pow
 
 
+def test_static_width_batched_over_tracks(track, orc):
+    """ReferencePath._compute_width for several tracks in one launch -- per-track base maps (the sim map with
+    different discs rasterised into it by the reference's add_obstacles rule) AND per-track paths (the sim path, the sim
+    path started elsewhere, a shorter open one: ragged n_wp) -- every width and border cell bit-exact against the oracle's
+    per-track call."""
+    import mpc_b200
+    from mpc_b200 import _lib
+    rng = np.random.default_rng(21)
+    T_ = 7
+    maps, tables, pts = [], [], []
+    for t in range(T_):
+        g = track.grid.copy()
+        for _ in range(int(rng.integers(0, 6))):
+            w = int(rng.integers(0, track.n_wp))
+            o = rng.uniform(-0.2, 0.2)
+            orc.add_obstacle(g, track.origin, track.res, track.wp_x[w] - o * np.sin(track.wp_psi[w]),
+                             track.wp_y[w] + o * np.cos(track.wp_psi[w]), rng.uniform(0.03, 0.08))
+        sl = slice(None) if t % 3 == 0 else (np.roll(np.arange(track.n_wp), -17 * t) if t % 3 == 1 else np.arange(20 * t, 20 * t + 90))
+        x, y, psi, kap = track.wp_x[sl], track.wp_y[sl], track.wp_psi[sl], track.wp_kappa[sl]
+        maps.append(g)
+        tables.append(_lib.path_table(x, y, psi, kap, None))
+        seg = np.hypot(np.diff(np.r_[x, x[0]]), np.diff(np.r_[y, y[0]]))
+        pts.append(orc.PathTables(x, y, psi, kap, np.ones(len(x)), seg, np.zeros((len(x), 4)), True))
+    eng = mpc_b200.Engine(precision=1)
+    ub, lb, border, err = eng.compute_width_batch(np.stack(maps), track.origin, track.res, tables, 0.23)
+    eng.close()
+    orc.set_pow_mode(False)
+    assert not err.any()
+    for t in range(T_):
+        st, ub_o, lb_o, border_o = orc.compute_width(maps[t], track.origin, track.res, pts[t], 0.23)
+        n = tables[t].shape[1]
+        assert st == 0
+        assert np.array_equal(ub[t, :n], ub_o) and np.array_equal(lb[t, :n], lb_o) and np.array_equal(border[t, :n], border_o), t
+        assert not ub[t, n:].any() and not border[t, n:].any()
+    assert len({tuple(ub[t, :90]) for t in range(T_)}) > 3   # the tracks really differ
+
+
 def test_rasteriser_bit_exact(engine_factory, track):
     R = load_golden("raycast_random.npz")
     eng = engine_factory(grid="free")
