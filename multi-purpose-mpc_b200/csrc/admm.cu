@@ -242,6 +242,16 @@ static bool force_pair_kernels() {
     return v;
 }
 
+// MPC_ADMM_KERNEL=quad selects the four-stages-per-lane kernel (admm_quad.cuh) where it applies (N + 1 <= 32, unbounded
+// e_psi / t rows); everything else falls through to the paired kernel
+static bool use_quad_kernel() {
+    static const bool v = [] {
+        const char* e = getenv("MPC_ADMM_KERNEL");
+        return e && e[0] == 'q';
+    }();
+    return v;
+}
+
 // CUDA loads a kernel's code on its first launch (lazy loading, ~15 ms): touch both fp32 solve kernels of this horizon
 // up front so that the engine's per-step choice between them never pays that inside a control step.
 void preload_solve_kernels(int precision, int N) {
@@ -251,6 +261,7 @@ void preload_solve_kernels(int precision, int N) {
     if (ns <= 16) cudaFuncGetAttributes(&fa, assemble_solve_kernel<float, 4, clamp_rlev<4, Tune<float>::rlev>(), Tune<float>::minb>);
     else if (ns <= 32) cudaFuncGetAttributes(&fa, assemble_solve_kernel<float, 5, clamp_rlev<5, Tune<float>::rlev>(), Tune<float>::minb>);
     preload_pair_kernels(N);
+    if (use_quad_kernel()) preload_quad_kernels(N);
     (void)cudaGetLastError();
 }
 
@@ -288,6 +299,10 @@ int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings
         if (ns <= 16) WARP_GO(double, 4); else if (ns <= 32) WARP_GO(double, 5);
         else if (ns <= 64) BLOCK_GO(double, 6, 64); else BLOCK_GO(double, 7, 128);
     } else if (use_pair_kernels() && ns <= 64 && !(prefer_stage && ns <= 32 && !force_pair_kernels())) {
+        if (use_quad_kernel() &&
+            launch_assemble_solve_quad(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s,
+                                       rollout_state, Ts, order) == 0)
+            return 0;
         return launch_assemble_solve_pair(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status,
                                           flags, B, s, rollout_state, Ts, order);
     } else {

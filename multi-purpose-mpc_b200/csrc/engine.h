@@ -55,6 +55,11 @@ int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings
 
 void preload_solve_kernels(int precision, int N);
 void preload_pair_kernels(int N);
+void preload_quad_kernels(int N);
+int launch_assemble_solve_quad(const MpcParams& mp, const AdmmSettings& st, const PathView& pv, const double* spatial,
+                               const int* wp_id, double* control, const double* ub, const double* lb, int* infeas,
+                               double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B, cudaStream_t s,
+                               double* rollout_state, double Ts, const int* order);
 // admm_pair.cu (fp32, N + 1 <= 64)
 int launch_solve_qp_pair(int N, const AdmmSettings& st, const double* Pd, const double* q, const double* Ax, const double* l,
                          const double* u, double* x_out, int* iters, int* status, int B, cudaStream_t s);

@@ -588,6 +588,13 @@ def test_solve_order_and_kernel_variant_do_not_change_the_answers(tmp_path):
     assert float((a["iters"] == c["iters"]).mean()) > 0.9
     assert np.abs(a["u"] - c["u"]).max() <= QP_TOL
     assert np.abs(a["state"] - c["state"]).max() <= QP_TOL
+    # (d) the four-stages-per-lane kernel (admm_quad.cuh): a third rounding of the same iteration, same bars
+    d = _run_variant(tmp_path, "quad", MPC_ADMM_KERNEL="quad")
+    assert np.array_equal(a["flags"], d["flags"]) and np.array_equal(a["qp_status"], d["qp_status"])
+    assert np.array_equal(a["iters"][solved], d["iters"][solved])
+    assert float((a["iters"] == d["iters"]).mean()) > 0.9
+    assert np.abs(a["u"] - d["u"]).max() <= QP_TOL
+    assert np.abs(a["state"] - d["state"]).max() <= QP_TOL
 
 
 @pytest.mark.parametrize("precision", [0, 1])
