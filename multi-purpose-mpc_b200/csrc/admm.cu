@@ -254,8 +254,9 @@ static bool use_quad_kernel() {
 
 // CUDA loads a kernel's code on its first launch (lazy loading, ~15 ms): touch both fp32 solve kernels of this horizon
 // up front so that the engine's per-step choice between them never pays that inside a control step.
-void preload_solve_kernels(int precision, int N) {
+void preload_solve_kernels(int precision, int N, int B) {
     if (precision != 0) return;
+    if (use_quad_kernel() && N + 1 <= 32) (void)reserve_quad_scratch(B);
     const int ns = N + 1;
     cudaFuncAttributes fa;
     if (ns <= 16) cudaFuncGetAttributes(&fa, assemble_solve_kernel<float, 4, clamp_rlev<4, Tune<float>::rlev>(), Tune<float>::minb>);

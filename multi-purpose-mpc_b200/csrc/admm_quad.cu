@@ -10,9 +10,22 @@
 namespace mpcb {
 
 constexpr int kQuadMinBlocks = 8;
-template <int LPS> constexpr size_t quad_smem_bytes() {
-    // (32 / LPS) scenarios x [kQuadRows][2 slices][LPS] f2, then [pcr_coef_f4][32 lanes] float4 (PCR coefficients)
-    return (size_t)32 * 2 * kQuadRows * sizeof(f2) + (size_t)PcrCoef<LPS>::kF4 * 32 * sizeof(float4);
+template <int LPS> constexpr size_t quad_smem_bytes() { return (size_t)QuadHot<LPS>::kF4 * 32 * sizeof(float4); }  // HOT columns
+constexpr size_t kQuadColdBytesPerWarp = (size_t)kQuadCold * 32 * sizeof(float4);
+
+// COLD columns of every warp of a launch: one process drives one GPU, so a single grow-only device buffer serves all
+// engines of the process (never shrunk; released with the context).  Grown outside stream capture only.
+static float4* g_cold = nullptr;
+static size_t g_cold_warps = 0;
+int reserve_quad_scratch(int B) {
+    const size_t warps = ((size_t)(B > 0 ? B : 0) + 3) / 4;
+    if (warps <= g_cold_warps) return 0;
+    float4* p = nullptr;
+    if (cudaMalloc(&p, warps * kQuadColdBytesPerWarp) != cudaSuccess) { (void)cudaGetLastError(); return MPC_E_CUDA; }
+    if (g_cold) cudaFree(g_cold);  // implicit device synchronisation: no launch is still using the old buffer
+    g_cold = p;
+    g_cold_warps = warps;
+    return 0;
 }
 
 // stage indices of the lane: slice 0 (E) = (4 gl, 4 gl + 2), slice 1 (O) = (4 gl + 1, 4 gl + 3)
@@ -86,7 +99,7 @@ assemble_solve_quad_kernel(MpcParams mp, AdmmSettings st, const f2 al2, const f2
                            const double* __restrict__ lb, int* __restrict__ infeas, double* __restrict__ u_out,
                            double* __restrict__ x_out, int* __restrict__ iters, int* __restrict__ qp_status,
                            int* __restrict__ flags, int B, double* __restrict__ rollout_state, double Ts,
-                           const int* __restrict__ order) {
+                           const int* __restrict__ order, float4* __restrict__ cold_base, int zero) {
     constexpr int G = 32 / LPS;
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * G + lane / LPS;
@@ -112,14 +125,14 @@ assemble_solve_quad_kernel(MpcParams mp, AdmmSettings st, const f2 al2, const f2
         pack_stages(s[sl], sA, sB);
     }
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    f2* sm = reinterpret_cast<f2*>(smem_raw) + (size_t)(lane / LPS) * kQuadRows * 2 * LPS;
-    float4* cf = reinterpret_cast<float4*>(smem_raw + (size_t)32 * 2 * kQuadRows * sizeof(f2)) + lane;
+    float4* hot = reinterpret_cast<float4*>(smem_raw) + lane;
+    float4* cold = cold_base + (size_t)blockIdx.x * kQuadCold * 32 + lane;
     auto emit = [&](const f2 (&w)[2][5], const SolveResult& r) {
         write_solution4(N, cm.gl, w, x_out ? x_out + (size_t)b * n : nullptr);
         const RolloutArgs ro{rollout_state, spatial, pv.kappa, wp, Ts, B};
         control_epilogue4<LPS>(cm, mp, w, r, cc, infeas, u_out, iters, qp_status, flags, b, fl, ro);
     };
-    admm_solve4<LPS>(cm, s, st, al2, nal2, n, sm, cf, live, emit);
+    admm_solve4<LPS>(cm, s, st, al2, nal2, n, hot, cold, live, zero, emit);
 }
 
 void preload_quad_kernels(int N) {
@@ -137,13 +150,18 @@ int launch_assemble_solve_quad(const MpcParams& mp, const AdmmSettings& st, cons
     const bool loose = mp.xmin[1] <= -kOsqpInfty && mp.xmax[1] >= kOsqpInfty && mp.xmin[2] <= -kOsqpInfty &&
                        mp.xmax[2] >= kOsqpInfty;
     if (ns > 32 || !loose) return MPC_E_UNSUPPORTED;
+    if (((size_t)B + 3) / 4 > g_cold_warps) {  // direct ABI call with a batch nobody reserved for: grow unless capturing
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return MPC_E_UNSUPPORTED;
+        if (reserve_quad_scratch(B)) return MPC_E_UNSUPPORTED;
+    }
     NvtxRange nvtx_("mpc:K1+K2 assemble_solve (four stages per lane, fp32)");
     constexpr int LPS = 8, per_block = 32 / LPS;
     const size_t smem = quad_smem_bytes<LPS>();
     { static int have_ = 0; ensure_dynamic_smem(assemble_solve_quad_kernel<LPS, kQuadMinBlocks>, have_, smem); }
     assemble_solve_quad_kernel<LPS, kQuadMinBlocks><<<(B + per_block - 1) / per_block, 32, smem, s>>>(
         mp, st, make_float2((float)st.alpha, (float)st.alpha), make_float2(-(float)st.alpha, -(float)st.alpha), pv, spatial, wp_id,
-        control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, rollout_state, Ts, order);
+        control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, rollout_state, Ts, order, g_cold, 0);
     return 0;
 }
 

@@ -633,7 +633,7 @@ int mpc_scenarios_init(mpc_engine* h, const double* h_state, int32_t B) {
     CUDA_OK(h->s_bucket.alloc(B));
     h->B = B;
     drop_graph(h);
-    preload_solve_kernels(h->cfg.precision, N);
+    preload_solve_kernels(h->cfg.precision, N, B);
     return mpc_scenarios_set_state(h, h_state, nullptr, nullptr);
 }
 
