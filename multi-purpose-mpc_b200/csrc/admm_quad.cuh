@@ -49,7 +49,9 @@ enum : int {
     kHL1 = 19,   // 9: level 1, 18 f2 = DE^-1 (00 01 02 11 12 22), U_E (0 1 2 3 4 8), U_O (0 1 2 3 4 8), two f2 per float4
     kHL2 = 28,   // 6: level 2, 24 floats = DA^-1 (6), UA (9), UB (9)
     kHEnd = 34,  // 4: PCR last level (9 floats) and the final D^-1 (00 01 02 11 12 22), 15 floats
-    kHPcr = 38,  // PcrCoef<LPS>::kF4: PCR levels 0 .. NLEV-2
+    kHC = 38,    // 3: c (the stage's own -1 entries of the dynamics rows, scaled)
+    kHE = 41,    // 3: e of the bound rows 0, 3, 4
+    kHPcr = 44,  // PcrCoef<LPS>::kF4: PCR levels 0 .. NLEV-2
 };
 template <int LPS> struct QuadHot { static constexpr int kF4 = kHPcr + PcrCoef<LPS>::kF4; };
 enum : int {
@@ -196,8 +198,14 @@ __device__ __forceinline__ void ruiz_scale4(const QuadComm<LPS>& cm, Stage2 (&s)
 // z = A w: zd (dynamics rows of each stage) and zb (bound rows 0, 3, 4; rows 1, 2 are loose)
 template <int LPS>
 __device__ __forceinline__ void A_apply4(const QuadComm<LPS>& cm, const Stage2 (&s)[2], const f2 (&w)[2][5], f2 (&zd)[2][3],
-                                         f2 (&zb)[2][5]) {
+                                         f2 (&zb)[2][5], const float4* hot, int zpin) {
     f2 o[2][3];
+    float4 c4[3], e4[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        c4[i] = lds128_after(hot + (kHC + i) * 32, w[0][0].x, zpin);
+        e4[i] = lds128_after(hot + (kHE + i) * 32, w[0][0].x, zpin);
+    }
 #pragma unroll
     for (int sl = 0; sl < 2; ++sl) {
         const f2* a = s[sl].a;
@@ -208,27 +216,33 @@ __device__ __forceinline__ void A_apply4(const QuadComm<LPS>& cm, const Stage2 (
 #pragma unroll
     for (int sl = 0; sl < 2; ++sl) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) zd[sl][i] = pfma(s[sl].c[i], w[sl][i], cm.prev_of(sl, o[0][i], o[1][i]));
-        zb[sl][0] = pmul(s[sl].e[0], w[sl][0]);
-        zb[sl][3] = pmul(s[sl].e[3], w[sl][3]);
-        zb[sl][4] = pmul(s[sl].e[4], w[sl][4]);
+        for (int i = 0; i < 3; ++i) zd[sl][i] = pfma(slice_of(c4[i], sl), w[sl][i], cm.prev_of(sl, o[0][i], o[1][i]));
+        zb[sl][0] = pmul(slice_of(e4[0], sl), w[sl][0]);
+        zb[sl][3] = pmul(slice_of(e4[1], sl), w[sl][3]);
+        zb[sl][4] = pmul(slice_of(e4[2], sl), w[sl][4]);
     }
 }
 
 // r = acc + A' y (yb[1], yb[2] are identically zero and not read)
 template <int LPS>
 __device__ __forceinline__ void At_apply4(const QuadComm<LPS>& cm, const Stage2 (&s)[2], const f2 (&yd)[2][3],
-                                          const f2 (&yb)[2][5], const f2 (&acc)[2][5], f2 (&r)[2][5]) {
+                                          const f2 (&yb)[2][5], const f2 (&acc)[2][5], f2 (&r)[2][5], const float4* hot, int zpin) {
+    float4 c4[3], e4[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        c4[i] = lds128_after(hot + (kHC + i) * 32, yd[0][0].x, zpin);
+        e4[i] = lds128_after(hot + (kHE + i) * 32, yd[0][0].x, zpin);
+    }
 #pragma unroll
     for (int sl = 0; sl < 2; ++sl) {
         const f2* a = s[sl].a;
         const f2 g0 = cm.next_of(sl, yd[0][0], yd[1][0]), g1 = cm.next_of(sl, yd[0][1], yd[1][1]),
                  g2 = cm.next_of(sl, yd[0][2], yd[1][2]);
-        const f2 r0 = pfma(a[4], g2, pfma(a[2], g1, pfma(a[0], g0, pfma(s[sl].c[0], yd[sl][0], pfma(s[sl].e[0], yb[sl][0], acc[sl][0])))));
-        const f2 r1 = pfma(a[3], g1, pfma(a[1], g0, pfma(s[sl].c[1], yd[sl][1], acc[sl][1])));
-        const f2 r2 = pfma(a[5], g2, pfma(s[sl].c[2], yd[sl][2], acc[sl][2]));
-        const f2 r3 = pfma(a[7], g2, pfma(s[sl].e[3], yb[sl][3], acc[sl][3]));
-        const f2 r4 = pfma(a[6], g1, pfma(s[sl].e[4], yb[sl][4], acc[sl][4]));
+        const f2 r0 = pfma(a[4], g2, pfma(a[2], g1, pfma(a[0], g0, pfma(slice_of(c4[0], sl), yd[sl][0], pfma(slice_of(e4[0], sl), yb[sl][0], acc[sl][0])))));
+        const f2 r1 = pfma(a[3], g1, pfma(a[1], g0, pfma(slice_of(c4[1], sl), yd[sl][1], acc[sl][1])));
+        const f2 r2 = pfma(a[5], g2, pfma(slice_of(c4[2], sl), yd[sl][2], acc[sl][2]));
+        const f2 r3 = pfma(a[7], g2, pfma(slice_of(e4[1], sl), yb[sl][3], acc[sl][3]));
+        const f2 r4 = pfma(a[6], g1, pfma(slice_of(e4[2], sl), yb[sl][4], acc[sl][4]));
         r[sl][0] = r0; r[sl][1] = r1; r[sl][2] = r2; r[sl][3] = r3; r[sl][4] = r4;
     }
 }
@@ -246,6 +260,9 @@ __device__ __forceinline__ void factorize4(const QuadComm<LPS>& cm, const Stage2
 #pragma unroll
     for (int i = 0; i < 5; ++i) P4[i] = lds128v(hot + (kHP + i) * 32);
     el4[0] = cold[(kCel + 0) * 32]; el4[1] = cold[(kCel + 1) * 32];
+    float4 c4[3], e4[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { c4[i] = lds128v(hot + (kHC + i) * 32); e4[i] = lds128v(hot + (kHE + i) * 32); }
 #pragma unroll
     for (int sl = 0; sl < 2; ++sl) {
         const f2* a = s[sl].a;
@@ -253,14 +270,14 @@ __device__ __forceinline__ void factorize4(const QuadComm<LPS>& cm, const Stage2
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
             const bool lz = (i == 1 || i == 2);  // loose rows: rho = rho_min, their e is COLD
-            const f2 ei = lz ? slice_of(el4[i == 1 ? 0 : 1], sl) : s[sl].e[i];
+            const f2 ei = lz ? slice_of(el4[i == 1 ? 0 : 1], sl) : slice_of(e4[i == 0 ? 0 : i - 2], sl);
             const f2 ri = lz ? bc((float)kRhoMin) : rho_row(codes, sl, i, rho, rdf);
             diag[i] = pfma(pmul(ri, ei), ei, padd(slice_of(P4[i], sl), sg));
         }
         f2 cn[3];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) cn[i] = cm.next_of(sl, s[0].c[i], s[1].c[i]);
-        const f2* c = s[sl].c;
+        for (int i = 0; i < 3; ++i) cn[i] = cm.next_of(sl, slice_of(c4[i], 0), slice_of(c4[i], 1));
+        const f2 c[3] = {slice_of(c4[0], sl), slice_of(c4[1], sl), slice_of(c4[2], sl)};
         D00[sl] = pfma(rd, pfma(a[4], a[4], pfma(a[2], a[2], pfma(a[0], a[0], pmul(c[0], c[0])))), diag[0]);
         D11[sl] = pfma(rd, pfma(a[3], a[3], pfma(a[1], a[1], pmul(c[1], c[1]))), diag[1]);
         D22[sl] = pfma(rd, pfma(a[5], a[5], pmul(c[2], c[2])), diag[2]);
@@ -667,6 +684,10 @@ __device__ __forceinline__ void admm_solve4(const QuadComm<LPS>& cm, Stage2 (&s)
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) { amax(nq_s, s[sl].q[i]); amax(nq_u, pmul(s[sl].q[i], prcp(s[sl].D[i]))); }
     }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) hot[(kHC + i) * 32] = both(s[0].c[i], s[1].c[i]);
+    hot[(kHE + 0) * 32] = both(s[0].e[0], s[1].e[0]); hot[(kHE + 1) * 32] = both(s[0].e[3], s[1].e[3]);
+    hot[(kHE + 2) * 32] = both(s[0].e[4], s[1].e[4]);
     const float cs0 = s[0].cs;
     C(kCmisc) = make_float4(cm.max(nq_s), cm.max(nq_u), cs0, 1.0f / cs0);
     smem_fence();
@@ -722,13 +743,13 @@ __device__ __forceinline__ void admm_solve4(const QuadComm<LPS>& cm, Stage2 (&s)
             rhs[0][i] = pfma(slice_of(P4, 0), x[0][i], u[0][i]);
             rhs[1][i] = pfma(slice_of(P4, 1), x[1][i], u[1][i]);
         }
-        At_apply4<LPS>(cm, s, td, tb, rhs, rhs);  // rhs = P x + u + A'(rho r);  S D = -rhs
+        At_apply4<LPS>(cm, s, td, tb, rhs, rhs, hot, zpin);  // rhs = P x + u + A'(rho r);  S D = -rhs
         kkt_solve4<LPS>(cm, f, rhs, dl, hot, zpin);
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
             for (int i = 0; i < 5; ++i) { dl[sl][i] = pmul(dl[sl][i], nal2); x[sl][i] = padd(x[sl][i], dl[sl][i]); }  // dl = alpha D
-        A_apply4<LPS>(cm, s, dl, s1d, s1b);
+        A_apply4<LPS>(cm, s, dl, s1d, s1b, hot, zpin);
         float4 lo4[3], hi4[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
@@ -787,7 +808,7 @@ __device__ __forceinline__ void admm_solve4(const QuadComm<LPS>& cm, Stage2 (&s)
                 }
             }
         }
-        At_apply4<LPS>(cm, s, ed, eb, u, u);
+        At_apply4<LPS>(cm, s, ed, eb, u, u, hot, zpin);
         if (keep) {
 #pragma unroll
             for (int i = 0; i < 5; ++i) C(kCdl + i) = both(dl[0][i], dl[1][i]);
@@ -807,7 +828,7 @@ __device__ __forceinline__ void admm_solve4(const QuadComm<LPS>& cm, Stage2 (&s)
         }
         if (can_check || can_adapt) {
             f2 axd[2][3], axb[2][5], zb[2][5];
-            A_apply4<LPS>(cm, s, x, axd, axb);
+            A_apply4<LPS>(cm, s, x, axd, axb, hot, zpin);
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const int i = j == 0 ? 0 : j + 2;
@@ -922,7 +943,7 @@ __device__ __forceinline__ void admm_solve4(const QuadComm<LPS>& cm, Stage2 (&s)
 #pragma unroll
                             for (int i = 0; i < 5; ++i) z5[sl][i] = zero;
                         float na = 0;
-                        At_apply4<LPS>(cm, s, ed, pyb, z5, atdy);
+                        At_apply4<LPS>(cm, s, ed, pyb, z5, atdy, hot, zpin);
 #pragma unroll
                         for (int i = 0; i < 5; ++i) {
                             const float4 D4 = C(kCD + i);
@@ -959,7 +980,7 @@ __device__ __forceinline__ void admm_solve4(const QuadComm<LPS>& cm, Stage2 (&s)
                     const bool cand = open && !dual_ok && !pinf && ndx > edi && qdx < -cs * edi * ndx && npdx < cs * edi * ndx;
                     if (GC::warp_any(cand)) {
                         f2 adxd[2][3], adxb[2][5];
-                        A_apply4<LPS>(cm, s, dl, adxd, adxb);
+                        A_apply4<LPS>(cm, s, dl, adxd, adxb, hot, zpin);
                         int bad = 0;
                         const float lim = edi * ndx;
                         const float4 e1 = C(kCel + 0), e2 = C(kCel + 1);
