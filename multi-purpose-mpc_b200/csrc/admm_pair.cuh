@@ -539,7 +539,9 @@ __device__ __forceinline__ void set_rho2(const f2* sm, int gl, float rho, float&
 //   0..2 d | 3..7 D | 8..10 Ed | 11..15 Eb | 16..20 1/D | 21..23 1/Ed | 24..28 1/Eb | 29..33 q | 34..38 e | 39..43 lo | 44..48 hi
 // and what the iteration reads once per pass (one LDS.64 each instead of a register pair held for the whole solve):
 //   49..53 P | 54 (|q|_scaled, |q|_unscaled) | 55 (c, 1/c)
-constexpr int kPairRows = 56;
+// and what the pass in front of a termination check leaves for the certificates (so that it is not carried in registers
+// from pass to pass):   56..60 alpha D (dx) | 61..63 dy of the dynamics rows | 64..68 dy of the bound rows
+constexpr int kPairRows = 69;
 
 // The OSQP loop.  ALL lanes of the warp call this together (every group = one scenario).  Control flow around
 // the collectives is warp-uniform: a branch that only some scenarios need is taken by the whole warp when ANY
@@ -609,9 +611,8 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
         done = true;
     };
     // one ADMM pass
-    f2 dl[5], ed[3], eb[5];
-    auto pass = [&](const bool first) __attribute__((always_inline)) {
-        f2 td[3], tb[5], rhs[5], s1d[3], s1b[5];
+    auto pass = [&](const bool first, const bool keep) __attribute__((always_inline)) {
+        f2 td[3], tb[5], rhs[5], s1d[3], s1b[5], dl[5], ed[3], eb[5];
 #pragma unroll
         for (int i = 0; i < 3; ++i) td[i] = MPC_Y_FORM ? pfma(rd, rdy[i], yd[i]) : pmul(rd, rdy[i]);
 #pragma unroll
@@ -677,6 +678,15 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
             for (int i = 0; i < 3; ++i) yd[i] = padd(yd[i], ed[i]);
         } else {
             At_apply2<LPS, LOOSE>(cm, s, ed, eb, u, u);
+        }
+        if (keep) {  // the next after_pass() checks: leave the certificates' operands in shared memory
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                sm[(56 + i) * LPS + gl] = dl[i];
+                if (!(LOOSE && (i == 1 || i == 2))) sm[(64 + i) * LPS + gl] = eb[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sm[(61 + i) * LPS + gl] = ed[i];
         }
     };
     // termination check / rho adaptation after a pass; returns true when every scenario of the warp is done
@@ -757,7 +767,11 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
                 bool pinf = false, dinf = false;
                 if (GC::warp_any(open && !prim_ok)) {  // is_primal_infeasible
                     const float epi = tol * (float)st.eps_prim_inf;
-                    f2 pyb[5];
+                    f2 pyb[5], ed[3], eb[5];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) ed[i] = ldsv(&sm[(61 + i) * LPS + gl]);
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) eb[i] = (LOOSE && (i == 1 || i == 2)) ? zero : ldsv(&sm[(64 + i) * LPS + gl]);
                     float ndy = 0, lhs = 0;
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
@@ -798,6 +812,9 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
                 }
                 if (GC::warp_any(open && !dual_ok && !pinf)) {  // is_dual_infeasible (dx = alpha D of this iteration)
                     const float edi = tol * (float)st.eps_dual_inf;
+                    f2 dl[5];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) dl[i] = ldsv(&sm[(56 + i) * LPS + gl]);
                     float ndx = 0, qdx = 0, npdx = 0;
 #pragma unroll
                     for (int i = 0; i < 5; ++i) {
@@ -873,7 +890,7 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
         return false;
     };
     for (iter = 1;; ++iter) {
-        if (phase == 0) pass(iter == 1);
+        if (phase == 0) pass(iter == 1, chk == 1 || iter >= st.max_iter);
         if (after_pass()) break;   // phase 2 always ends here: every scenario still open is finished with -2
         if (phase == 1 || (phase == 0 && iter >= st.max_iter)) {
             // the last pass was a check pass iff check_termination divides max_iter
