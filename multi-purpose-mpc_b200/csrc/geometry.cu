@@ -483,9 +483,13 @@ __device__ void plan_solve_order(const int* __restrict__ prev_iters, const int* 
 
 // MODE 0: no staging (global / L1 reads).  MODE 1: one grid shared by all scenarios, staged once per CTA
 // (whole grid, one TMA bulk copy) and reused by all warps and all scenarios the CTA loops over.
-// MODE 2: per-scenario grids, each warp stages the row span of its own scenario.
+// MODE 2: per-scenario grids, each warp stages the row span of its own scenario (A/B switch MPC_RAYCAST_MODE=2; the
+// default for per-scenario grids is MODE 0 at 32 warps per SM, which is faster -- see raycast_plan).
+#ifndef MPC_RAYCAST_MINB0
+#define MPC_RAYCAST_MINB0 4
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(MODE == 1 ? 896 : 256, 1)
+__global__ void __launch_bounds__(MODE == 1 ? 896 : 256, MODE == 0 ? MPC_RAYCAST_MINB0 : 1)
 raycast_kernel(RaycastArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const GridView& g = a.g;
@@ -750,7 +754,12 @@ int raycast_plan(const GridView& g, int N, bool shared_grid, int max_rows, bool 
         *warps = 8;
         *smem = raycast_smem_bytes(g, N, 1, g.H, 8);
         if (*smem <= kLimit / 2) return 1;
-    } else if (rowspan_ok) {
+    } else if (rowspan_ok && getenv("MPC_RAYCAST_MODE") && getenv("MPC_RAYCAST_MODE")[0] == '2') {
+        // Per-scenario grids, row span staged per warp by TMA: an A/B switch since round 2.  Measured at 8192 obstacle
+        // scenarios (profiles/r2_raycast_modes.txt): 164 us staged against 114 us for the direct walk below.  The kernel is
+        // a latency-bound instruction stream (5.9 k instructions per scenario, DRAM 7 % busy): staging serialises copy ->
+        // wait -> replay inside a warp and its 23 KB slab per warp caps an SM at 8 warps, while the direct walk keeps eight
+        // independent table entries per lane in flight on 32 warps per SM (64 registers) and hides the DRAM latency itself.
         for (int w = 4; w >= 1; w >>= 1) {
             *warps = w; *stage_rows = max_rows;
             *smem = raycast_smem_bytes(g, N, 2, max_rows, w);

@@ -231,8 +231,14 @@ def test_raycast_modes_agree(engine_factory, track):
     per = engine_factory(grid="free")                              # per-scenario copies of the same nine discs
     per.set_obstacles(np.tile(track.obstacles, (B, 1)), np.arange(B + 1, dtype=np.int32) * len(track.obstacles))
     u1, l1 = run(shared, 30)
-    u2, l2 = run(per, 30)                                          # mode 2 (row span table is for N = 30)
-    u0, l0 = run(per, 29)                                          # mode 0 (no row span table for N = 29)
+    os.environ["MPC_RAYCAST_MODE"] = "2"                           # the TMA-staged variant is an A/B switch (read per launch)
+    try:
+        u2, l2 = run(per, 30)                                      # mode 2 (row span table is for N = 30)
+    finally:
+        os.environ.pop("MPC_RAYCAST_MODE")
+    u0, l0 = run(per, 30)                                          # mode 0: the default for per-scenario grids
+    assert np.array_equal(u2, u0) and np.array_equal(l2, l0)
+    u0, l0 = run(per, 29)                                          # mode 0 at a horizon without a row span table
     assert np.array_equal(u1, u2) and np.array_equal(l1, l2)
     assert np.array_equal(u1[:, :29], u0) and np.array_equal(l1[:, :29], l0)
 
