@@ -408,6 +408,108 @@ __device__ __forceinline__ int replay_ray(const uint32_t* __restrict__ base, con
     return nseg;
 }
 
+// The slow exact path of a ray with more free segments than its scratch holds (kMaxSeg; the reference's list is unbounded,
+// rp.py:466-520): ONE lane walks ray k again and stores the segments number first .. first + kMaxSeg - 1.
+__device__ __noinline__ void refill_segments(const uint32_t* __restrict__ base, const uint32_t* __restrict__ cells, int n_wp,
+                                             int k, int len, int ubx, int uby, int pitch, double ox, double oy, double res,
+                                             double min_width, short4* segs, int first) {
+    uint32_t uo = 0xffffffffu, pending = 0u;
+    int nseg = 0;
+    for (int i = 0; i < len; ++i) {
+        const uint32_t e = __ldg(cells + (size_t)i * n_wp + k);
+        const uint32_t x = (base[e >> 6] >> (e & 31u)) & 1u;
+        const uint32_t term = (~x | (e >> 5)) & 1u;
+        pending |= x;
+        if (term & pending) {
+            const uint32_t w = e >> 6;
+            const int y = (int)(w / (uint32_t)pitch), xx = (int)(w % (uint32_t)pitch) * 32 + (int)(e & 31u);
+            int ux = ubx, uy = uby;
+            if (uo != 0xffffffffu) {
+                const uint32_t wu = uo >> 6;
+                uy = (int)(wu / (uint32_t)pitch); ux = (int)(wu % (uint32_t)pitch) * 32 + (int)(uo & 31u);
+            }
+            const double uxw = ((double)ux + 0.5) * res + ox, uyw = ((double)uy + 0.5) * res + oy;
+            const double lxw = ((double)xx + 0.5) * res + ox, lyw = ((double)y + 0.5) * res + oy;
+            if (sqrt(sq(uxw - lxw) + sq(uyw - lyw)) > min_width) {
+                if (nseg >= first && nseg < first + kMaxSeg) segs[nseg - first] = make_short4((short)ux, (short)uy, (short)xx, (short)y);
+                ++nseg;
+            }
+            pending = 0u;
+        }
+        uo = term ? e : uo;
+    }
+}
+
+// The two out-of-line routines below take scalars only (a reference to the kernel's GridView / PathView would force a copy of
+// the structs into local memory on every path).
+struct WinGeom { int pitch, n_wp; double ox, oy, res, min_width; };
+__device__ __forceinline__ void m2w_s(const WinGeom& w, int dx, int dy, double& x, double& y) {
+    x = ((double)dx + 0.5) * w.res + w.ox;  // map.py:98
+    y = ((double)dy + 0.5) * w.res + w.oy;  // map.py:99
+}
+// rp.py:552-586 for a ray with more than kMaxSeg free segments: the whole warp takes the candidates kMaxSeg at a time (lane 0
+// re-walks the ray for every window after the first) and keeps the first minimum of the mean end-point distance.
+__device__ __noinline__ void pick_nearest_windowed(int pitch, int n_wp, double ox, double oy, double res, double min_width,
+                                                   const uint32_t* base, const uint32_t* cells, int len, int k, int nseg, int sx,
+                                                   int sy, short4* segs, double upx, double upy, double lpx, double lpy, int lane,
+                                                   double* out4) {
+    const WinGeom w{pitch, n_wp, ox, oy, res, min_width};
+    double best_md = INFINITY, bux = 0, buy = 0, blx = 0, bly = 0;
+    for (int w0 = 0; w0 < nseg; w0 += kMaxSeg) {
+        if (w0 > 0) {
+            if (lane == 0) refill_segments(base, cells, n_wp, k, len, sx, sy, pitch, ox, oy, res, min_width, segs, w0);
+            __syncwarp();
+        }
+        const int cnt = nseg - w0 < kMaxSeg ? nseg - w0 : kMaxSeg;
+        double md = INFINITY, ubx = 0, uby = 0, lbx = 0, lby = 0;
+        if (lane < cnt) {
+            const short4 s4 = segs[lane];
+            m2w_s(w, s4.x, s4.y, ubx, uby);
+            m2w_s(w, s4.z, s4.w, lbx, lby);
+            md = (sqrt(sq(ubx - upx) + sq(uby - upy)) + sqrt(sq(lbx - lpx) + sq(lby - lpy))) / 2;  // rp.py:576-578
+        }
+        double wmd = md;
+        int wl = lane;
+#pragma unroll
+        for (int s = 4; s > 0; s >>= 1) {
+            const double o = __shfl_xor_sync(0xffffffffu, wmd, s);
+            const int ol = __shfl_xor_sync(0xffffffffu, wl, s);
+            if (o < wmd || (o == wmd && ol < wl)) { wmd = o; wl = ol; }
+        }
+        wl = __shfl_sync(0xffffffffu, wl, 0);
+        wmd = __shfl_sync(0xffffffffu, wmd, 0);
+        const double cux = __shfl_sync(0xffffffffu, ubx, wl), cuy = __shfl_sync(0xffffffffu, uby, wl);
+        const double clx = __shfl_sync(0xffffffffu, lbx, wl), cly = __shfl_sync(0xffffffffu, lby, wl);
+        if (wmd < best_md) { best_md = wmd; bux = cux; buy = cuy; blx = clx; bly = cly; }  // first minimum over the windows
+        __syncwarp();
+    }
+    if (lane == 0) { out4[0] = bux; out4[1] = buy; out4[2] = blx; out4[3] = bly; }
+    __syncwarp();
+}
+
+// rp.py:545-548 (largest free segment of the first waypoint, first maximum) for a ray with more than kMaxSeg free segments;
+// leaves the winner in segs[0]
+__device__ __noinline__ void pick_largest_windowed(int pitch, int n_wp, double ox, double oy, double res, double min_width,
+                                                   const uint32_t* base, const uint32_t* cells, int len, int k, int nseg, int sx,
+                                                   int sy, short4* segs) {
+    const WinGeom w{pitch, n_wp, ox, oy, res, min_width};
+    double bl = -1.0;
+    short4 best = segs[0];
+    for (int w0 = 0; w0 < nseg; w0 += kMaxSeg) {
+        if (w0 > 0) refill_segments(base, cells, n_wp, k, len, sx, sy, pitch, ox, oy, res, min_width, segs, w0);
+        const int cnt = nseg - w0 < kMaxSeg ? nseg - w0 : kMaxSeg;
+        for (int i = 0; i < cnt; ++i) {
+            const short4 c4 = segs[i];
+            double ux, uy, lx, ly;
+            m2w_s(w, c4.x, c4.y, ux, uy);
+            m2w_s(w, c4.z, c4.w, lx, ly);
+            const double l = sqrt(sq(ux - lx) + sq(uy - ly));
+            if (l > bl) { bl = l; best = c4; }
+        }
+    }
+    segs[0] = best;
+}
+
 struct RaycastArgs {
     const uint32_t* grids;
     size_t grid_stride_words;  // 0: every scenario uses the same grid
@@ -568,10 +670,7 @@ raycast_kernel(RaycastArgs a) {
             w2m(g, pv.border[4 * k], pv.border[4 * k + 1], ubx, uby);  // the ray's start cell (rp.py:478, 488)
             const int nseg = replay_ray(base, a.ray_cells, pv.n_wp, k, max_len_warp, ubx, uby, g.pitch_words, g.ox, g.oy,
                                         g.res, a.min_width, segs + (n < N ? n : 0) * kMaxSeg);
-            if (n < N) {
-                if (nseg > kMaxSeg) status |= MPC_ST_INDEX_ERROR;
-                nsegs[n] = nseg;
-            }
+            if (n < N) nsegs[n] = nseg;  // may exceed kMaxSeg: such a ray is re-walked window by window below
         }
         __syncwarp();
         if (nsegs[0] == 0) status |= MPC_ST_NO_SEGMENT;  // rp.py:547 max([]) -> ValueError
@@ -591,19 +690,24 @@ raycast_kernel(RaycastArgs a) {
             double ubx, uby, lbx, lby;
             if (nseg == 0) { ubx = pv.x[k]; uby = pv.y[k]; lbx = ubx; lby = uby; }  // rp.py:595
             else {
-                int best = 0;
-                if (n == 0 && nseg > 1) {  // largest segment, first maximum (rp.py:545-548)
+                short4 s4 = segs[n * kMaxSeg];
+                if (n == 0 && nseg > kMaxSeg) {
+                    int sx, sy;
+                    w2m(g, pv.border[4 * k], pv.border[4 * k + 1], sx, sy);
+                    pick_largest_windowed(g.pitch_words, pv.n_wp, g.ox, g.oy, g.res, a.min_width, base, a.ray_cells, a.ray_len[k], k,
+                                          nseg, sx, sy, segs + n * kMaxSeg);
+                    s4 = segs[n * kMaxSeg];
+                } else if (n == 0 && nseg > 1) {  // largest segment, first maximum (rp.py:545-548)
                     double bl = -1.0;
                     for (int i = 0; i < nseg; ++i) {
-                        const short4 s4 = segs[n * kMaxSeg + i];
+                        const short4 c4 = segs[n * kMaxSeg + i];
                         double ux, uy, lx, ly;
-                        m2w(g, s4.x, s4.y, ux, uy);
-                        m2w(g, s4.z, s4.w, lx, ly);
+                        m2w(g, c4.x, c4.y, ux, uy);
+                        m2w(g, c4.z, c4.w, lx, ly);
                         const double l = sqrt(sq(ux - lx) + sq(uy - ly));
-                        if (l > bl) { bl = l; best = i; }
+                        if (l > bl) { bl = l; s4 = c4; }
                     }
                 }
-                const short4 s4 = segs[n * kMaxSeg + best];
                 m2w(g, s4.x, s4.y, ubx, uby);
                 m2w(g, s4.z, s4.w, lbx, lby);
             }
@@ -627,26 +731,40 @@ raycast_kernel(RaycastArgs a) {
             const double upy = prev_cells[4 * (n - 1) + 1] + ds * pv.cos_psi[kp];  // rp.py:560 (quirk Q2)
             const double lpx = prev_cells[4 * (n - 1) + 2] + ds * pv.sin_psi[kp];  // rp.py:561
             const double lpy = prev_cells[4 * (n - 1) + 3] + ds * pv.sin_psi[kp];  // rp.py:562
-            double md = INFINITY, ubx = 0, uby = 0, lbx = 0, lby = 0;
-            if (lane < nseg) {
-                const short4 s4 = segs[n * kMaxSeg + lane];
-                m2w(g, s4.x, s4.y, ubx, uby);
-                m2w(g, s4.z, s4.w, lbx, lby);
-                const double d_ub = sqrt(sq(ubx - upx) + sq(uby - upy));  // rp.py:576
-                const double d_lb = sqrt(sq(lbx - lpx) + sq(lby - lpy));  // rp.py:577
-                md = (d_ub + d_lb) / 2;
-            }
-            double wmd = md;
-            int wl = lane;
+            // candidates live in lanes 0 .. kMaxSeg-1
+            double bux, buy, blx, bly;
+            if (nseg <= kMaxSeg) {
+                double md = INFINITY, ubx = 0, uby = 0, lbx = 0, lby = 0;
+                if (lane < nseg) {
+                    const short4 s4 = segs[n * kMaxSeg + lane];
+                    m2w(g, s4.x, s4.y, ubx, uby);
+                    m2w(g, s4.z, s4.w, lbx, lby);
+                    const double d_ub = sqrt(sq(ubx - upx) + sq(uby - upy));  // rp.py:576
+                    const double d_lb = sqrt(sq(lbx - lpx) + sq(lby - lpy));  // rp.py:577
+                    md = (d_ub + d_lb) / 2;
+                }
+                double wmd = md;
+                int wl = lane;
 #pragma unroll
-            for (int s = 4; s > 0; s >>= 1) {  // kMaxSeg = 8 candidates live in lanes 0..7
-                const double o = __shfl_xor_sync(0xffffffffu, wmd, s);
-                const int ol = __shfl_xor_sync(0xffffffffu, wl, s);
-                if (o < wmd || (o == wmd && ol < wl)) { wmd = o; wl = ol; }  // list.index(min()) = first minimum
+                for (int s = 4; s > 0; s >>= 1) {
+                    const double o = __shfl_xor_sync(0xffffffffu, wmd, s);
+                    const int ol = __shfl_xor_sync(0xffffffffu, wl, s);
+                    if (o < wmd || (o == wmd && ol < wl)) { wmd = o; wl = ol; }  // list.index(min()) = first minimum
+                }
+                wl = __shfl_sync(0xffffffffu, wl, 0);
+                bux = __shfl_sync(0xffffffffu, ubx, wl); buy = __shfl_sync(0xffffffffu, uby, wl);
+                blx = __shfl_sync(0xffffffffu, lbx, wl); bly = __shfl_sync(0xffffffffu, lby, wl);
+            } else {  // more free segments than the scratch holds: slow exact path, window by window
+                int sx, sy;
+                w2m(g, pv.border[4 * k], pv.border[4 * k + 1], sx, sy);
+                double* out4 = prev_cells + 4 * n;  // scratch of this waypoint, overwritten with its cells right below
+                pick_nearest_windowed(g.pitch_words, pv.n_wp, g.ox, g.oy, g.res, a.min_width, base, a.ray_cells, a.ray_len[k], k,
+                                      nseg, sx, sy, segs + n * kMaxSeg, upx, upy, lpx, lpy, lane, out4);
+                bux = out4[0]; buy = out4[1]; blx = out4[2]; bly = out4[3];
+                __syncwarp();
             }
-            wl = __shfl_sync(0xffffffffu, wl, 0);
-            if (lane == wl) {
-                const RayOut o = finalize_wp(pv, k, ubx, uby, lbx, lby, a.sm);
+            if (lane == 0) {
+                const RayOut o = finalize_wp(pv, k, bux, buy, blx, bly, a.sm);
                 ub_o[n] = o.ub;
                 lb_o[n] = o.lb;
 #pragma unroll

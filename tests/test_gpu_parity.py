@@ -1063,3 +1063,49 @@ def test_raycast_dense_obstacle_fuzz(engine_factory, track, orc, orc_path):
         assert np.array_equal(ub_o, ub[b]) and np.array_equal(lb_o, lb[b]), b
         n_multi += int((ub_o - lb_o < 0.25).any())
     assert n_multi > B // 4  # the clutter does narrow the corridor in a good share of the horizons
+
+
+def test_raycast_more_free_segments_than_the_scratch_holds(engine_factory, track, orc, orc_path):
+    """The reference keeps an unbounded list of free segments per ray (rp.py:466-520); the kernel keeps eight per ray in shared
+    memory and re-walks a ray window by window when it closes more (slow exact path, no scenario is dropped for it).  A
+    striped map -- every sixth column and every sixth row of the corridor occupied -- with min_width = 1.5 cm gives rays
+    with up to fifteen free segments; all three grid-access modes, widths bit-exact against the oracle."""
+    import torch
+    g = track.grid.copy()
+    g[:, ::6] = 0
+    g[::6, :] = 0
+    sm, mw = 0.06 / np.sqrt(2), 0.015
+    wid = np.arange(0, track.n_wp, 3).astype(np.int32)
+    B = len(wid)
+    orc.set_pow_mode(False)
+    ref, ok = [], []
+    for w in wid:
+        st, ub_o, lb_o, _ = orc.update_path_constraints(g, track.origin, track.res, orc_path, int(w) + 1, 30, mw, sm)
+        ref.append((ub_o, lb_o)); ok.append(st == 0)
+    assert sum(ok) > B // 2
+    # count the free segments of the first ray of a few horizons on the host to be sure the slow path is exercised
+    def run(eng):
+        ub = torch.zeros((B, 30), dtype=torch.float64, device=_dev())
+        lb = torch.zeros_like(ub)
+        fl = torch.zeros(B, dtype=torch.int32, device=_dev())
+        eng.update_path_constraints(_t(wid, torch.int32), 1, 30, mw, sm, ub, lb, None, fl)
+        eng.sync()
+        return ub.cpu().numpy(), lb.cpu().numpy(), fl.cpu().numpy()
+    shared = engine_factory(grid="free")
+    shared.set_base_grid(g, track.origin, track.res)
+    per = engine_factory(grid="free")
+    per.set_base_grid(g, track.origin, track.res)
+    per.set_obstacles(np.zeros((0, 3)), np.zeros(B + 1, np.int32))     # per-scenario copies of the striped map
+    outs = [run(shared), run(per)]
+    os.environ["MPC_RAYCAST_MODE"] = "2"
+    try:
+        outs.append(run(per))
+    finally:
+        os.environ.pop("MPC_RAYCAST_MODE")
+    for ub, lb, fl in outs:
+        for i in range(B):
+            if not ok[i]:
+                assert fl[i] & 4, (i, fl[i])
+                continue
+            assert fl[i] == 0, (i, fl[i])                              # in particular no MPC_ST_INDEX_ERROR any more
+            assert np.array_equal(ub[i], ref[i][0]) and np.array_equal(lb[i], ref[i][1]), i
