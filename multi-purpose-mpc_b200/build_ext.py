@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmpc_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
-UNITS = [("admm.cu", ["-DMPC_TUNING_VARIANTS"] if os.environ.get("MPC_TUNING_VARIANTS") else []), ("admm_pair.cu", []), ("admm_quad.cu", []), ("geometry.cu", ["-fmad=false"]), ("engine.cu", ["-fmad=false"]),
+UNITS = [("admm.cu", ["-DMPC_TUNING_VARIANTS"] if os.environ.get("MPC_TUNING_VARIANTS") else []), ("admm_pair.cu", []), ("admm_quad.cu", []), ("admm_tm.cu", []), ("geometry.cu", ["-fmad=false"]), ("engine.cu", ["-fmad=false"]),
          ("speed_profile.cu", ["-fmad=false"])]
 
 

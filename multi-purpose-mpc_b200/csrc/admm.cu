@@ -252,11 +252,21 @@ static bool use_quad_kernel() {
     return v;
 }
 
+// MPC_ADMM_KERNEL=tm selects the tensor-memory variant of the paired kernel (admm_tm.cuh) where it applies
+static bool use_tm_kernel() {
+    static const bool v = [] {
+        const char* e = getenv("MPC_ADMM_KERNEL");
+        return e && e[0] == 't';
+    }();
+    return v;
+}
+
 // CUDA loads a kernel's code on its first launch (lazy loading, ~15 ms): touch both fp32 solve kernels of this horizon
 // up front so that the engine's per-step choice between them never pays that inside a control step.
 void preload_solve_kernels(int precision, int N, int B) {
     if (precision != 0) return;
     if (use_quad_kernel() && N + 1 <= 32) (void)reserve_quad_scratch(B);
+    if (use_tm_kernel() && N + 1 <= 32) { (void)reserve_tm_scratch(B); preload_tm_kernels(N); }
     const int ns = N + 1;
     cudaFuncAttributes fa;
     if (ns <= 16) cudaFuncGetAttributes(&fa, assemble_solve_kernel<float, 4, clamp_rlev<4, Tune<float>::rlev>(), Tune<float>::minb>);
@@ -300,6 +310,10 @@ int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings
         if (ns <= 16) WARP_GO(double, 4); else if (ns <= 32) WARP_GO(double, 5);
         else if (ns <= 64) BLOCK_GO(double, 6, 64); else BLOCK_GO(double, 7, 128);
     } else if (use_pair_kernels() && ns <= 64 && !(prefer_stage && ns <= 32 && !force_pair_kernels())) {
+        if (use_tm_kernel() &&
+            launch_assemble_solve_tm(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s,
+                                     rollout_state, Ts, order) == 0)
+            return 0;
         if (use_quad_kernel() &&
             launch_assemble_solve_quad(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s,
                                        rollout_state, Ts, order) == 0)

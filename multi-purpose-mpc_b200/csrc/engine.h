@@ -56,6 +56,12 @@ int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings
 void preload_solve_kernels(int precision, int N, int B = 0);
 void preload_pair_kernels(int N);
 void preload_quad_kernels(int N);
+void preload_tm_kernels(int N);
+int reserve_tm_scratch(int B);   // global-memory rows of the tensor-memory variant (admm_tm.cu), outside capture
+int launch_assemble_solve_tm(const MpcParams& mp, const AdmmSettings& st, const PathView& pv, const double* spatial,
+                             const int* wp_id, double* control, const double* ub, const double* lb, int* infeas, double* u_out,
+                             double* x_out, int* iters, int* qp_status, int* flags, int B, cudaStream_t s, double* rollout_state,
+                             double Ts, const int* order);
 int reserve_quad_scratch(int B);  // global-memory columns of the four-stages-per-lane kernel (admm_quad.cu), outside capture
 int launch_assemble_solve_quad(const MpcParams& mp, const AdmmSettings& st, const PathView& pv, const double* spatial,
                                const int* wp_id, double* control, const double* ub, const double* lb, int* infeas,

@@ -594,6 +594,14 @@ def test_solve_order_and_kernel_variant_do_not_change_the_answers(tmp_path):
     assert float((a["iters"] == c["iters"]).mean()) > 0.9
     assert np.abs(a["u"] - c["u"]).max() <= QP_TOL
     assert np.abs(a["state"] - c["state"]).max() <= QP_TOL
+    # (e) the tensor-memory variant of the paired kernel (admm_tm.cuh): the paired kernel's pass fed from TMEM instead of
+    #     registers -- identical on QPs that OSQP solves; the (separately compiled) check / re-factorisation code rounds a few
+    #     expressions differently, which can move the certificate of an infeasible QP by a check
+    t = _run_variant(tmp_path, "tm", MPC_ADMM_KERNEL="tm")
+    assert np.array_equal(a["flags"], t["flags"]) and np.array_equal(a["qp_status"], t["qp_status"])
+    assert np.array_equal(a["iters"][solved], t["iters"][solved])
+    assert float((a["iters"] == t["iters"]).mean()) > 0.99
+    assert np.abs(a["u"] - t["u"]).max() <= QP_TOL / 4 and np.abs(a["state"] - t["state"]).max() <= QP_TOL / 4
     # (d) the four-stages-per-lane kernel (admm_quad.cuh): a third rounding of the same iteration, same bars
     d = _run_variant(tmp_path, "quad", MPC_ADMM_KERNEL="quad")
     assert np.array_equal(a["flags"], d["flags"]) and np.array_equal(a["qp_status"], d["qp_status"])
