@@ -1117,3 +1117,40 @@ def test_raycast_more_free_segments_than_the_scratch_holds(engine_factory, track
                 continue
             assert fl[i] == 0, (i, fl[i])                              # in particular no MPC_ST_INDEX_ERROR any more
             assert np.array_equal(ub[i], ref[i][0]) and np.array_equal(lb[i], ref[i][1]), i
+
+
+def test_width_table_follows_the_base_grid(engine_factory, track, orc, orc_path):
+    """The width table (update_path_constraints of every waypoint horizon, ray-cast once on a shared grid) must be rebuilt
+    whenever something it depends on changes: a closed-loop step after mpc_set_base_grid sees the NEW map, after
+    mpc_set_obstacles the per-scenario maps (no table), after clearing them the table again -- always the oracle's widths."""
+    TF = load_golden("teacher_forced.npz")
+    B = 24
+    st0 = np.ascontiguousarray(TF["state"][:B].T)
+    sm = 0.06 / np.sqrt(2)
+    orc.set_pow_mode(False)
+    eng = engine_factory(grid="free", precision=1)
+
+    def check(grid_of):
+        eng.scenarios_init(st0)
+        eng.step()
+        o = eng.scenarios_read()
+        for b in range(B):
+            stt, ub_o, lb_o, _ = orc.update_path_constraints(grid_of(b), track.origin, track.res, orc_path, int(o["wp_id"][b]) + 1, 30,
+                                                             2 * sm, sm)
+            if stt == 0:
+                assert np.array_equal(ub_o, o["ub"][b]) and np.array_equal(lb_o, o["lb"][b]), b
+            else:
+                assert o["flags"][b] & 4, b
+        return o
+
+    a = check(lambda b: track.grid)                      # free map: table built on first use
+    eng.set_base_grid(track.grid_obs, track.origin, track.res)
+    c = check(lambda b: track.grid_obs)                  # the nine obstacles: table rebuilt
+    assert not np.array_equal(a["ub"], c["ub"])
+    rng = np.random.default_rng(5)
+    obs = np.array([(track.wp_x[w], track.wp_y[w], 0.05) for w in rng.integers(0, track.n_wp, B)])
+    eng.set_obstacles(obs, np.arange(B + 1, dtype=np.int32))
+    check(lambda b: eng.get_grid(b))                     # per-scenario maps: every car ray-casts its own
+    eng.set_obstacles(None, None)
+    d = check(lambda b: track.grid_obs)                  # back on the shared map
+    assert np.array_equal(c["ub"], d["ub"]) and np.array_equal(c["lb"], d["lb"])
