@@ -890,7 +890,13 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
         return false;
     };
     for (iter = 1;; ++iter) {
+#ifdef MPC_QUAD_MARK   // PMTRIG markers around the pass (tools/sass_pass.py)
+        asm volatile("pmevent 1;");
+#endif
         if (phase == 0) pass(iter == 1, chk == 1 || iter >= st.max_iter);
+#ifdef MPC_QUAD_MARK
+        asm volatile("pmevent 2;");
+#endif
         if (after_pass()) break;   // phase 2 always ends here: every scenario still open is finished with -2
         if (phase == 1 || (phase == 0 && iter >= st.max_iter)) {
             // the last pass was a check pass iff check_termination divides max_iter
