@@ -195,6 +195,10 @@ int mpc_rollout(mpc_engine *h, double *d_state, const double *d_spatial, const i
 int mpc_scenarios_init(mpc_engine *h, const double *h_state, int32_t B);
 int mpc_scenarios_set_state(mpc_engine *h, const double *h_state, const double *h_control,
                             const int32_t *h_infeas);
+/* Restores the per-scenario step flags (MPC_ST_* bitmask, int32[B]) after mpc_scenarios_set_state, which clears them: a
+ * caller that continues a fleet keeps its DEAD / FINISHED scenarios out of the loop (the reference's exit(1) at
+ * MPC.py:218-220 and the end of `while car.s < length`, simulation.py:134, are final). */
+int mpc_scenarios_set_flags(mpc_engine *h, const int32_t *h_flags);
 int mpc_step(mpc_engine *h);
 int mpc_run_closed_loop(mpc_engine *h, int32_t max_steps, double *h_stats);
 /* host-buffer variant of one step (the e2e path): H2D of h_state[4][B], step, D2H of h_u_out[B][2]

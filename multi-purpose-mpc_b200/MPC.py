@@ -205,8 +205,13 @@ class BatchedMPC(_MPCBase):
         self._sync_tables()
         eng.sync()
         st = b.state.cpu().numpy()
-        eng.scenarios_init(st)
+        if getattr(self, "_loop_B", None) != self.B:   # (re)allocate the engine-owned fleet only when its size changes:
+            eng.scenarios_init(st)                     # scenarios_init drops the captured graphs
+            self._loop_B = self.B
         eng.scenarios_set_state(st, b.control.cpu().numpy(), b.infeas.cpu().numpy())
+        # scenarios that died (N-1 infeasible QPs in a row: the reference exits, MPC.py:218-220) or finished their lap in an
+        # earlier call stay out of the loop; the per-step bits (fallback, ...) are recomputed by the next step
+        eng.scenarios_set_flags(b.flags.cpu().numpy() & (2 | 32))
         stats = eng.run_closed_loop(max_steps)
         out = eng.scenarios_read()
         t = b.torch

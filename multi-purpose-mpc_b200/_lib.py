@@ -39,7 +39,7 @@ EXPORTS = [
     "mpc_engine_set_stream", "mpc_engine_update_config", "mpc_engine_sync", "mpc_set_path", "mpc_set_vref",
     "mpc_set_base_grid", "mpc_set_obstacles", "mpc_get_grid", "mpc_compute_width", "mpc_compute_width_batch", "mpc_localize_t2s",
     "mpc_raycast", "mpc_update_path_constraints", "mpc_assemble_solve", "mpc_solve_qp", "mpc_rollout",
-    "mpc_scenarios_init", "mpc_scenarios_set_state", "mpc_step", "mpc_run_closed_loop", "mpc_step_host",
+    "mpc_scenarios_init", "mpc_scenarios_set_state", "mpc_scenarios_set_flags", "mpc_step", "mpc_run_closed_loop", "mpc_step_host",
     "mpc_scenarios_ptrs", "mpc_scenarios_read", "mpc_launch_count", "mpc_set_profiling", "mpc_get_profile",
     "mpc_speed_profile", "mpc_speed_profile_batch", "mpc_predict_xy", "mpc_host_io",
 ]
@@ -88,6 +88,7 @@ def load():
     L.mpc_rollout.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int32]
     L.mpc_scenarios_init.argtypes = [vp, c_double_p, C.c_int32]
     L.mpc_scenarios_set_state.argtypes = [vp, c_double_p, c_double_p, c_int_p]
+    L.mpc_scenarios_set_flags.argtypes = [vp, c_int_p]
     L.mpc_step.argtypes = [vp]
     L.mpc_run_closed_loop.argtypes = [vp, C.c_int32, c_double_p]
     L.mpc_step_host.argtypes = [vp, c_double_p, c_double_p, c_int_p]
@@ -308,6 +309,11 @@ class Engine:
         i = None if infeas is None else np.ascontiguousarray(infeas, dtype=np.int32)
         _check(self.L.mpc_scenarios_set_state(self.h, None if s is None else _dp(s), None if c is None else _dp(c),
                                               None if i is None else i.ctypes.data_as(c_int_p)))
+
+    def scenarios_set_flags(self, flags):
+        f = np.ascontiguousarray(flags, dtype=np.int32)
+        assert f.shape == (self.B,)
+        _check(self.L.mpc_scenarios_set_flags(self.h, _ip(f)))
 
     def step(self):
         _check(self.L.mpc_step(self.h))

@@ -661,6 +661,14 @@ int mpc_scenarios_set_state(mpc_engine* h, const double* h_state, const double* 
     return 0;
 }
 
+int mpc_scenarios_set_flags(mpc_engine* h, const int32_t* h_flags) {
+    if (!h || h->B <= 0) return fail(MPC_E_STATE, "mpc_scenarios_init first");
+    if (!h_flags) return fail(MPC_E_INVALID, "null flags");
+    CUDA_OK(cudaMemcpyAsync(h->s_flags.p, h_flags, (size_t)h->B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 // One closed-loop step (simulation.py:137-140).  Fused path (default): two kernels -- K4a+K3 (localise inside the
 // raycast kernel) and K1+K2+K4b (rollout behind the solve).  Profiling path: the four kernels of the ABI, bracketed by
 // events, so that each gets its own duration.

@@ -106,3 +106,14 @@ def test_batched_api_matches_single_car(sim, track):
     stats = bm.run_closed_loop(10)
     assert stats["scenario_steps"] == 10 * B and stats["dead"] == 0
     assert np.abs(cars.s.cpu().numpy() - C1["state_after"][12][3]).max() <= 1e-6
+    # a second call continues the fleet: scenarios that died or finished in an earlier call stay out of the loop (the
+    # reference's exit(1) at MPC.py:218-220 is final) and the engine-owned buffers are not re-allocated
+    bm.flags[3] = 2                                                            # MPC_ST_DEAD
+    pose3 = cars.state[:, 3].clone() if hasattr(cars, "state") else None
+    s_before = cars.s.cpu().numpy().copy()
+    stats2 = bm.run_closed_loop(5)
+    s_after = cars.s.cpu().numpy()
+    assert s_after[3] == s_before[3] and (s_after[np.arange(B) != 3] > s_before[np.arange(B) != 3]).all()
+    assert int(bm.flags[3].item()) & 2
+    assert stats2["scenario_steps"] == 5 * (B - 1)
+    assert np.abs(s_after[0] - C1["state_after"][17][3]) <= 1e-6
