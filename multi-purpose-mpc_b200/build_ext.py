@@ -44,8 +44,10 @@ def build(force=False, verbose=False):
         if p.wait() != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if force or procs or _newer(objs, OUT):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", OUT] + objs + ["-ccbin", "/usr/bin/g++", "-ldl"]
+        tmp = OUT + ".tmp.%d" % os.getpid()   # link next to the target, then rename: the library is replaced atomically
+        cmd = [nvcc] + ARCH + ["-shared", "-o", tmp] + objs + ["-ccbin", "/usr/bin/g++", "-ldl"]
         subprocess.check_call(cmd)
+        os.replace(tmp, OUT)
     return OUT
 
 

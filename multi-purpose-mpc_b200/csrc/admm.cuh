@@ -502,10 +502,11 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
     // 2 / 3 / 4), else reports max-iter (-2).  Both go through the same check code below.
     int phase = 0;
     T tol = T(1);
-    T dl[5] = {0, 0, 0, 0, 0}, ed[3] = {0, 0, 0}, eb[5] = {0, 0, 0, 0, 0};
     for (iter = 1;; ++iter) {
-        bool can_check = true, can_adapt = false;
-        if (phase == 0) {
+        // dl, ed, eb (the certificates' operands) live for ONE trip of this loop: the end-of-loop checks of OSQP run in the
+        // trip of the last pass (inner loop below), so nothing is carried from pass to pass for them
+        T dl[5], ed[3], eb[5];
+        bool can_check, can_adapt;
         T g[5], td[3], tb[5];
 #pragma unroll
         for (int i = 0; i < 3; ++i) td[i] = rd * rdy[i];
@@ -546,7 +547,7 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
         can_check = (--chk == 0); can_adapt = (--adp == 0);
         if (can_check) chk = st.check_termination;
         if (can_adapt) adp = st.adaptive_rho_interval;
-        }  // phase == 0
+        for (;;) {  // one trip per pass; after the last pass up to two more (phases 1 and 2)
         if (can_check || can_adapt) {
             T axd[3], axb[5], aty[5], zd[3], D[5], Ed[3], Eb[5], Di[5], Edi[3], Ebi[5], dx[5], dyd[3], dyb[5];
 #pragma unroll
@@ -675,7 +676,12 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
             const bool checked = phase == 0 && st.check_termination > 0 && (st.max_iter % st.check_termination == 0);
             phase = (phase == 1 || checked) ? 2 : 1;
             if (phase == 2) tol = T(10);
+            can_check = true; can_adapt = false;
+            continue;
         }
+        break;
+        }  // check trips
+        if (status != 0) break;
     }
     T D[5];
 #pragma unroll
