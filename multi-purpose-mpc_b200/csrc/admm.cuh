@@ -167,7 +167,8 @@ template <typename T, int NLEV, int RLEV> struct Factor {
 
 // per-scenario shared constants (read only at termination checks): [29][W]
 //   0..2 d | 3..7 D | 8..10 Ed | 11..15 Eb | 16..20 1/D | 21..23 1/Ed | 24..28 1/Eb
-constexpr int kConstRows = 29;
+//   29..33 alpha D | 34..36 dy (dynamics rows) | 37..41 dy (bound rows) of the LAST pass, for OSQP's end-of-loop checks
+constexpr int kConstRows = 42;
 template <int NLEV, int RLEV> __host__ __device__ constexpr int smem_rows() { return kConstRows + 18 * (NLEV - RLEV); }
 
 template <typename T> __device__ __forceinline__ T tfma(T a, T b, T c);
@@ -497,57 +498,12 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
     int status = 0, iter = 0;
     int chk = st.check_termination > 0 ? st.check_termination : -1;
     int adp = st.adaptive_rho_interval > 0 ? st.adaptive_rho_interval : -1;
-    // phase 0 = iterating; after max_iter passes OSQP (osqp.c, after its main loop) runs a NORMAL termination check if
-    // the last pass was not a check pass (phase 1) and then the APPROXIMATE one (phase 2: every tolerance x 10, statuses
-    // 2 / 3 / 4), else reports max-iter (-2).  Both go through the same check code below.
-    int phase = 0;
-    T tol = T(1);
-    for (iter = 1;; ++iter) {
-        // dl, ed, eb (the certificates' operands) live for ONE trip of this loop: the end-of-loop checks of OSQP run in the
-        // trip of the last pass (inner loop below), so nothing is carried from pass to pass for them
-        T dl[5], ed[3], eb[5];
-        bool can_check, can_adapt;
-        T g[5], td[3], tb[5];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) td[i] = rd * rdy[i];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) tb[i] = rb[i] * rbd[i];
-        At_apply(cm, s, td, tb, g);
-#pragma unroll
-        for (int i = 0; i < 5; ++i) g[i] = -((tfma(s.P[i], x[i], s.q[i]) + ty[i]) + g[i]);
-        kkt_solve<T, NLEV, RLEV>(cm, f, g, lane, dl);
-        T add[3], adb[5];
-        A_apply(cm, s, dl, lane, add, adb);
-        // ed, eb: dual steps dy = rho ((v - z_prev) - (z_new - z_prev))
-#pragma unroll
-        for (int i = 0; i < 5; ++i) x[i] = tfma(alpha, dl[i], x[i]);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const T wv = alpha * (rdy[i] + add[i]);  // v - z_prev
-            ed[i] = rd * (wv - stepd[i]);  // dy of the dynamics rows (their y itself is never needed)
-            rdy[i] = tfma(alpha, add[i], rdy[i]) - stepd[i];
-            stepd[i] = T(0);
-        }
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const T wv = alpha * (rbd[i] + adb[i]);
-            const T zn = tmin(tmax(tfma(rbi[i], yb[i], zb[i] + wv), s.lo[i]), s.hi[i]);
-            const T step = zn - zb[i];
-            eb[i] = rb[i] * (wv - step);  // dy of the bound rows
-            yb[i] += eb[i];
-            rbd[i] = tfma(alpha, adb[i], rbd[i]) - step;
-            zb[i] = zn;
-        }
-        {
-            T dty[5];
-            At_apply(cm, s, ed, eb, dty);
-#pragma unroll
-            for (int i = 0; i < 5; ++i) ty[i] += dty[i];
-        }
-        can_check = (--chk == 0); can_adapt = (--adp == 0);
-        if (can_check) chk = st.check_termination;
-        if (can_adapt) adp = st.adaptive_rho_interval;
-        for (;;) {  // one trip per pass; after the last pass up to two more (phases 1 and 2)
+    // The termination check / rho adaptation after a pass.  After max_iter passes OSQP (osqp.c, after its main loop) runs a
+    // NORMAL termination check if the last pass was not a check pass (phase 1) and then the APPROXIMATE one (phase 2: every
+    // tolerance x 10, statuses 2 / 3 / 4), else reports max-iter (-2): the same code, instantiated once more behind the loop
+    // so that the loop itself carries nothing for it.  Returns the OSQP status, 0 = keep iterating.
+    auto check = [&](const int phase, const T tol, const T* dl, const T* ed, const T* eb, const bool can_check,
+                     const bool can_adapt) __attribute__((always_inline)) -> int {
         if (can_check || can_adapt) {
             T axd[3], axb[5], aty[5], zd[3], D[5], Ed[3], Eb[5], Di[5], Edi[3], Ebi[5], dx[5], dyd[3], dyb[5];
 #pragma unroll
@@ -591,11 +547,11 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
             nz_s = cm.max(nz_s); nz_u = cm.max(nz_u); nax_s = cm.max(nax_s); nax_u = cm.max(nax_u);
             npx_s = cm.max(npx_s); npx_u = cm.max(npx_u); naty_s = cm.max(naty_s); naty_u = cm.max(naty_u);
             if (can_check) {
-                if (pr_u > T(kOsqpInfty) || du_u > T(kOsqpInfty)) { status = -7; break; }
+                if (pr_u > T(kOsqpInfty) || du_u > T(kOsqpInfty)) return -7;
                 const T eps_prim = tol * (T(st.eps_abs) + T(st.eps_rel) * tmax(nz_u, nax_u));
                 const T eps_dual = tol * (T(st.eps_abs) + T(st.eps_rel) * cinv * tmax(tmax(nq_u, naty_u), npx_u));
                 const bool prim_ok = pr_u < eps_prim, dual_ok = du_u < eps_dual;
-                if (prim_ok && dual_ok) { status = phase == 2 ? 2 : 1; break; }
+                if (prim_ok && dual_ok) return phase == 2 ? 2 : 1;
                 bool pinf = false, dinf = false;
                 if (!prim_ok) {  // is_primal_infeasible
                     const T epi = tol * T(st.eps_prim_inf);
@@ -655,8 +611,8 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
                         }
                     }
                 }
-                if (pinf) { status = phase == 2 ? 3 : -3; break; }
-                if (dinf) { status = phase == 2 ? 4 : -4; break; }
+                if (pinf) return phase == 2 ? 3 : -3;
+                if (dinf) return phase == 2 ? 4 : -4;
             }
             if (can_adapt) {  // adapt_rho / compute_rho_estimate on the scaled residuals
                 T pn = pr_s / (tmax(nz_s, nax_s) + T(1e-10));
@@ -670,23 +626,75 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
                 }
             }
         }
-        if (phase == 2) { status = -2; break; }
-        if (phase == 1 || (phase == 0 && iter >= st.max_iter)) {
-            // the last pass was a check pass iff check_termination divides max_iter
-            const bool checked = phase == 0 && st.check_termination > 0 && (st.max_iter % st.check_termination == 0);
-            phase = (phase == 1 || checked) ? 2 : 1;
-            if (phase == 2) tol = T(10);
-            can_check = true; can_adapt = false;
-            continue;
+        return 0;
+    };
+    for (iter = 1; iter <= st.max_iter; ++iter) {
+        T dl[5], ed[3], eb[5];
+        T g[5], td[3], tb[5];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) td[i] = rd * rdy[i];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) tb[i] = rb[i] * rbd[i];
+        At_apply(cm, s, td, tb, g);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) g[i] = -((tfma(s.P[i], x[i], s.q[i]) + ty[i]) + g[i]);
+        kkt_solve<T, NLEV, RLEV>(cm, f, g, lane, dl);
+        T add[3], adb[5];
+        A_apply(cm, s, dl, lane, add, adb);
+        // ed, eb: dual steps dy = rho ((v - z_prev) - (z_new - z_prev))
+#pragma unroll
+        for (int i = 0; i < 5; ++i) x[i] = tfma(alpha, dl[i], x[i]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const T wv = alpha * (rdy[i] + add[i]);  // v - z_prev
+            ed[i] = rd * (wv - stepd[i]);  // dy of the dynamics rows (their y itself is never needed)
+            rdy[i] = tfma(alpha, add[i], rdy[i]) - stepd[i];
+            stepd[i] = T(0);
         }
-        break;
-        }  // check trips
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const T wv = alpha * (rbd[i] + adb[i]);
+            const T zn = tmin(tmax(tfma(rbi[i], yb[i], zb[i] + wv), s.lo[i]), s.hi[i]);
+            const T step = zn - zb[i];
+            eb[i] = rb[i] * (wv - step);  // dy of the bound rows
+            yb[i] += eb[i];
+            rbd[i] = tfma(alpha, adb[i], rbd[i]) - step;
+            zb[i] = zn;
+        }
+        {
+            T dty[5];
+            At_apply(cm, s, ed, eb, dty);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) ty[i] += dty[i];
+        }
+        const bool can_check = (--chk == 0), can_adapt = (--adp == 0);
+        if (can_check) chk = st.check_termination;
+        if (can_adapt) adp = st.adaptive_rho_interval;
+        status = check(0, T(1), dl, ed, eb, can_check, can_adapt);
         if (status != 0) break;
+        if (iter == st.max_iter) {  // the end-of-loop checks need this pass's steps
+#pragma unroll
+            for (int i = 0; i < 5; ++i) { sm[(29 + i) * W + lane] = dl[i]; sm[(37 + i) * W + lane] = eb[i]; }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sm[(34 + i) * W + lane] = ed[i];
+        }
+    }
+    if (status == 0) {
+        iter = st.max_iter;
+        T dl[5], ed[3], eb[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { dl[i] = sm[(29 + i) * W + lane]; eb[i] = sm[(37 + i) * W + lane]; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ed[i] = sm[(34 + i) * W + lane];
+        // the last pass was a check pass iff check_termination divides max_iter
+        const bool checked = st.check_termination > 0 && (st.max_iter % st.check_termination == 0);
+        if (!checked) status = check(1, T(1), dl, ed, eb, true, false);
+        if (status == 0) status = check(2, T(10), dl, ed, eb, true, false);
+        if (status == 0) status = -2;
     }
     T D[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) D[i] = sm[(3 + i) * W + lane];
-    if (phase != 0) iter = st.max_iter;
     // OSQP stores no solution for the (approximately) infeasible and the non-convex statuses (NaN vectors)
     const bool nan_out = (status == -3 || status == -4 || status == -7 || status == 3 || status == 4);
 #pragma unroll
