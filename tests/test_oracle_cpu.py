@@ -237,3 +237,32 @@ def test_full_step_matches_reference_lap(orc, track, orc_path):
             assert np.allclose(r["state"], C1["state_after"][k], rtol=1e-12, atol=1e-12)
     finally:
         orc.set_pow_mode(False)
+
+
+def test_osqp_restatement_against_the_real_solver_when_installed(orc):
+    """Independent tier for the one third-party algorithm on the hot path: when a real `osqp` wheel is importable (it is not
+    in the offline image, so this normally skips) the restatement must agree with it on the golden QPs -- same status, the
+    primal solution within 1e-3 after the H1 projection at eps 1e-5 (the north-star's setting, where the solver's own
+    adaptive-rho timing heuristic no longer matters), and iteration counts within one termination check at the defaults
+    with adaptive_rho_interval pinned to 25 on both sides."""
+    osqp = pytest.importorskip("osqp")
+    from conftest import h1_split
+    TF = load_golden("teacher_forced.npz")
+    Ap, Ai = fixed_pattern(30)
+    ks = [k for k in range(len(TF["qp_status"])) if TF["qp_status"][k] == 1][:12]
+    for eps, tol_it in ((1e-3, 25), (1e-5, None)):
+        xo, ito, sto = orc.batch_qp_solve(30, TF["qp_Pd"][ks], TF["qp_q"][ks], Ap, Ai, TF["qp_Ax"][ks], TF["qp_l"][ks],
+                                          TF["qp_u"][ks], eps_abs=eps, eps_rel=eps)
+        for j, k in enumerate(ks):
+            P = sparse.diags(TF["qp_Pd"][k]).tocsc()
+            A = sparse.csc_matrix((TF["qp_Ax"][k], Ai, Ap), shape=(246, 153))
+            m = osqp.OSQP()
+            m.setup(P=P, q=TF["qp_q"][k], A=A, l=TF["qp_l"][k], u=TF["qp_u"][k], verbose=False, eps_abs=eps, eps_rel=eps,
+                    adaptive_rho_interval=25, polish=False)
+            r = m.solve()
+            assert r.info.status_val == sto[j]
+            if tol_it is not None:
+                assert abs(r.info.iter - ito[j]) <= tol_it
+            rem, null = h1_split(30, TF["qp_Pd"][k][None], TF["qp_Ax"][k][None], (r.x - xo[j])[None])
+            if eps < 1e-4:
+                assert np.abs(rem).max() <= 1e-3
