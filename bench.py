@@ -795,9 +795,12 @@ def main():
         e2.close()
 
     # ---------------- end-to-end arm: host buffers, H2D + D2H inside the timed region -------------------
-    # inputs (state[4][B]) and results (state, u[B][2], flags[B]) live in page-locked HOST memory; every step is
-    # H2D + localise/raycast + assemble/solve/rollout + D2H, submitted as one graph launch by mpc_step_host
-    def time_e2e(pinned):
+    # inputs (state[4][B]) and results (state, u[B][2], flags[B]) live in page-locked HOST memory; every step is one graph
+    # launch by mpc_step_host.  Default graph: the first kernel reads the state out of the caller's memory over PCIe and the
+    # solve kernel's epilogue stores state / u / flags back into it (no staging copies); MPC_HOST_IO=copy: H2D node +
+    # kernels + D2H node.  Both move the same bytes per step and give the same bits (tests/test_gpu_parity.py).
+    def time_e2e(pinned, io_mode="kernel"):
+        os.environ["MPC_HOST_IO"] = io_mode
         eng = make_engine()
         if pinned:
             hs, hu, hf = eng.host_io()
@@ -821,10 +824,13 @@ def main():
         chk = np.array(hu, copy=True)  # the results are read on the host
         eng.close()
         return Bg * args.steps / dt, chk
-    e2e_value, e2e_chk = time_e2e(True)
-    e2e_pageable, e2e_chk2 = time_e2e(False)
-    assert np.array_equal(e2e_chk, e2e_chk2, equal_nan=True) and np.nansum(np.abs(e2e_chk)) > 0, \
-        "pinned and pageable step_host disagree"
+    io_mode_default = os.environ.get("MPC_HOST_IO", "kernel")
+    e2e_value, e2e_chk = time_e2e(True, io_mode_default)
+    e2e_copy_nodes, e2e_chk3 = time_e2e(True, "copy")
+    e2e_pageable, e2e_chk2 = time_e2e(False, io_mode_default)
+    os.environ["MPC_HOST_IO"] = io_mode_default
+    assert np.array_equal(e2e_chk, e2e_chk2, equal_nan=True) and np.array_equal(e2e_chk, e2e_chk3, equal_nan=True) and \
+        np.nansum(np.abs(e2e_chk)) > 0, "step_host paths (kernel-side host I/O, copy nodes, pageable) disagree"
 
     agg = D.allreduce_stats(stats)  # the one collective of the job: statistics only
 
@@ -868,8 +874,13 @@ def main():
             "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * B * 8),
                     "d2h_bytes_per_step": int(6 * B * 8 + 4 * B),
-                    "path": "mpc_step_host on page-locked host buffers (H2D + 2 kernels + D2H = one graph launch), host "
-                            "wall clock around each of the K synchronous calls, summed", "pageable_buffers_value": e2e_pageable},
+                    "path": "mpc_step_host on page-locked host buffers, one graph launch per step: the first kernel reads the "
+                            "state from the host buffer over PCIe, the solve kernel's epilogue writes state / u / flags into "
+                            "the host buffers (no staging copies); host wall clock around each of the K synchronous calls, "
+                            "summed" if io_mode_default[0] != "c" else
+                            "mpc_step_host on page-locked host buffers (H2D + 2 kernels + D2H = one graph launch), host "
+                            "wall clock around each of the K synchronous calls, summed",
+                    "with_copy_nodes_value": e2e_copy_nodes, "pageable_buffers_value": e2e_pageable},
             "gpu_launches": int(launches),
             "kernel_ms": kernel_ms,
             "roofline": {"kernel": ("assemble_solve_pair_kernel<16,loose> (K1+K2+K4b, paired-stage fp32)" if os.environ.get("MPC_ADMM_KERNEL", "p")[0] != "s"

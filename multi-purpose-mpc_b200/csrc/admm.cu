@@ -68,6 +68,7 @@ __device__ __forceinline__ void control_epilogue(Comm& cm, const MpcParams& mp, 
         if (flags) flags[b] = fl;
         if (iters) iters[b] = r.iters;
         if (qp_status) qp_status[b] = r.status;
+        store_host_results(ro, u_out, b, fl);
     }
 }
 
@@ -104,7 +105,7 @@ assemble_solve_kernel(MpcParams mp, AdmmSettings st, PathView pv, const double* 
                       const int* __restrict__ wp_id, double* __restrict__ control, const double* __restrict__ ub,
                       const double* __restrict__ lb, int* __restrict__ infeas, double* __restrict__ u_out,
                       double* __restrict__ x_out, int* __restrict__ iters, int* __restrict__ qp_status,
-                      int* __restrict__ flags, int B, double* __restrict__ rollout_state, double Ts) {
+                      int* __restrict__ flags, int B, double* __restrict__ rollout_state, double Ts, HostIO hio) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (b >= B) return;
@@ -121,7 +122,7 @@ assemble_solve_kernel(MpcParams mp, AdmmSettings st, PathView pv, const double* 
     T w[5];
     const SolveResult r = admm_solve<T, NLEV, RLEV>(cm, s, st, lane, N + 1, n, sm, w);
     write_solution<T>(N, lane, w, x_out ? x_out + (size_t)b * n : nullptr);
-    const RolloutArgs ro{rollout_state, spatial, pv.kappa, wp_id[b], Ts, B};
+    const RolloutArgs ro{rollout_state, spatial, pv.kappa, wp_id[b], Ts, B, hio.state, hio.u, hio.flags};
     control_epilogue<T>(cm, mp, lane, w, r, cc, infeas, u_out, iters, qp_status, flags, b, fl, ro);
 }
 
@@ -157,7 +158,7 @@ assemble_solve_block_kernel(MpcParams mp, AdmmSettings st, PathView pv, const do
                             const int* __restrict__ wp_id, double* __restrict__ control, const double* __restrict__ ub,
                             const double* __restrict__ lb, int* __restrict__ infeas, double* __restrict__ u_out,
                             double* __restrict__ x_out, int* __restrict__ iters, int* __restrict__ qp_status,
-                            int* __restrict__ flags, int B, double* __restrict__ rollout_state, double Ts) {
+                            int* __restrict__ flags, int B, double* __restrict__ rollout_state, double Ts, HostIO hio) {
     const int lane = threadIdx.x, b = blockIdx.x;
     if (b >= B) return;
     const int fl = flags ? flags[b] : 0;
@@ -173,7 +174,7 @@ assemble_solve_block_kernel(MpcParams mp, AdmmSettings st, PathView pv, const do
     T w[5];
     const SolveResult r = admm_solve<T, NLEV, 0>(cm, s, st, lane, N + 1, n, sm, w);
     write_solution<T>(N, lane, w, x_out ? x_out + (size_t)b * n : nullptr);
-    const RolloutArgs ro{rollout_state, spatial, pv.kappa, wp_id[b], Ts, B};
+    const RolloutArgs ro{rollout_state, spatial, pv.kappa, wp_id[b], Ts, B, hio.state, hio.u, hio.flags};
     control_epilogue<T>(cm, mp, lane, w, r, cc, infeas, u_out, iters, qp_status, flags, b, fl, ro);
 }
 
@@ -195,13 +196,13 @@ template <typename T, int NLEV, int RLEV, int MINB>
 static void assemble_solve_launch(const MpcParams& mp, const AdmmSettings& st, const PathView& pv, const double* spatial,
                                   const int* wp_id, double* control, const double* ub, const double* lb, int* infeas,
                                   double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
-                                  cudaStream_t s, double* rs, double Ts) {
+                                  cudaStream_t s, double* rs, double Ts, HostIO hio) {
     constexpr int R = clamp_rlev<NLEV, RLEV>();
     const int grid = (B + kWarpsPerBlock - 1) / kWarpsPerBlock, block = 32 * kWarpsPerBlock;
     const size_t smem = warp_smem_bytes<T, NLEV, R>();
     { static int have_ = 0; ensure_dynamic_smem(assemble_solve_kernel<T, NLEV, R, MINB>, have_, smem); }
     assemble_solve_kernel<T, NLEV, R, MINB><<<grid, block, smem, s>>>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas,
-                                                                      u_out, x_out, iters, qp_status, flags, B, rs, Ts);
+                                                                      u_out, x_out, iters, qp_status, flags, B, rs, Ts, hio);
 }
 
 template <typename T, int NLEV, int NT>
@@ -217,11 +218,11 @@ template <typename T, int NLEV, int NT>
 static void assemble_solve_block_launch(const MpcParams& mp, const AdmmSettings& st, const PathView& pv,
                                         const double* spatial, const int* wp_id, double* control, const double* ub,
                                         const double* lb, int* infeas, double* u_out, double* x_out, int* iters,
-                                        int* qp_status, int* flags, int B, cudaStream_t s, double* rs, double Ts) {
+                                        int* qp_status, int* flags, int B, cudaStream_t s, double* rs, double Ts, HostIO hio) {
     const size_t smem = block_smem_bytes<T, NLEV, NT>();
     { static int have_ = 0; ensure_dynamic_smem(assemble_solve_block_kernel<T, NLEV, NT>, have_, smem); }
     assemble_solve_block_kernel<T, NLEV, NT><<<B, NT, smem, s>>>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out,
-                                                                x_out, iters, qp_status, flags, B, rs, Ts);
+                                                                x_out, iters, qp_status, flags, B, rs, Ts, hio);
 }
 
 // MPC_ADMM_KERNEL=stage selects the lane-per-stage fp32 kernels (admm.cuh) instead of the paired-stage ones
@@ -297,13 +298,16 @@ int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* 
     return 0;
 }
 
+bool solve_writes_host_io() { return !(use_tm_kernel() || use_quad_kernel()); }
+
 int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings& st, const PathView& pv,
                           const double* spatial, const int* wp_id, double* control, const double* ub, const double* lb,
                           int* infeas, double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
-                          cudaStream_t s, double* rollout_state, double Ts, const int* order, bool prefer_stage) {
+                          cudaStream_t s, double* rollout_state, double Ts, const int* order, bool prefer_stage, const HostIO* host_io) {
+    const HostIO hio = host_io ? *host_io : HostIO{nullptr, nullptr, nullptr};
     NvtxRange nvtx_("mpc:K1+K2 assemble_solve");
-#define WARP_GO(T_, L_) assemble_solve_launch<T_, L_, Tune<T_>::rlev, Tune<T_>::minb>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts)
-#define BLOCK_GO(T_, L_, NT_) assemble_solve_block_launch<T_, L_, NT_>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts)
+#define WARP_GO(T_, L_) assemble_solve_launch<T_, L_, Tune<T_>::rlev, Tune<T_>::minb>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts, hio)
+#define BLOCK_GO(T_, L_, NT_) assemble_solve_block_launch<T_, L_, NT_>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts, hio)
     const int ns = mp.N + 1;
     if (ns > 128) return MPC_E_UNSUPPORTED;
     if (precision == 1) {
@@ -319,7 +323,7 @@ int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings
                                        rollout_state, Ts, order) == 0)
             return 0;
         return launch_assemble_solve_pair(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status,
-                                          flags, B, s, rollout_state, Ts, order);
+                                          flags, B, s, rollout_state, Ts, order, host_io);
     } else {
         if (ns <= 16) WARP_GO(float, 4); else if (ns <= 32) WARP_GO(float, 5);
         else if (ns <= 64) BLOCK_GO(float, 6, 64); else BLOCK_GO(float, 7, 128);

@@ -27,6 +27,21 @@ struct RolloutArgs {  // non-null state: fuse the rollout of this scenario behin
     int wp;
     double Ts;
     int B;
+    // mpc_step_host on page-locked buffers: the epilogue also stores the step's results straight into the caller's host memory
+    // (device-mapped pointers; null = off), so that the step needs no device-to-host copy node
+    double* host_state = nullptr;
+    double* host_u = nullptr;
+    int* host_flags = nullptr;
 };
+
+// lane 0 of a scenario, after the epilogue wrote the device copies
+__device__ __forceinline__ void store_host_results(const RolloutArgs& ro, const double* u_out, int b, int fl) {
+    if (ro.host_flags) ro.host_flags[b] = fl;
+    if (ro.host_u) { ro.host_u[2 * (size_t)b] = u_out[2 * (size_t)b]; ro.host_u[2 * (size_t)b + 1] = u_out[2 * (size_t)b + 1]; }
+    if (ro.host_state && ro.state) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ro.host_state[(size_t)k * ro.B + b] = ro.state[(size_t)k * ro.B + b];
+    }
+}
 
 }  // namespace mpcb

@@ -70,6 +70,7 @@ __device__ __forceinline__ void control_epilogue2(const GroupComm<LPS>& cm, cons
         if (flags) flags[b] = fl;
         if (iters) iters[b] = r.iters;
         if (qp_status) qp_status[b] = r.status;
+        store_host_results(ro, u_out, b, fl);
     }
 }
 
@@ -123,7 +124,7 @@ assemble_solve_pair_kernel(MpcParams mp, AdmmSettings st, const f2 al2, const f2
                            const double* __restrict__ lb, int* __restrict__ infeas, double* __restrict__ u_out,
                            double* __restrict__ x_out, int* __restrict__ iters, int* __restrict__ qp_status,
                            int* __restrict__ flags, int B, double* __restrict__ rollout_state, double Ts,
-                           const int* __restrict__ order) {
+                           const int* __restrict__ order, HostIO hio) {
     constexpr int G = 32 / LPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = (blockIdx.x * kPairWarpsPerBlock + warp) * G + lane / LPS;
@@ -152,7 +153,7 @@ assemble_solve_pair_kernel(MpcParams mp, AdmmSettings st, const f2 al2, const f2
     f2* sm = reinterpret_cast<f2*>(smem_raw) + ((size_t)warp * G + lane / LPS) * kPairRows * LPS;
     auto emit = [&](const f2 w[5], const SolveResult& r) {
         write_solution2(N, cm.gl, w, x_out ? x_out + (size_t)b * n : nullptr);
-        const RolloutArgs ro{rollout_state, spatial, pv.kappa, wp, Ts, B};
+        const RolloutArgs ro{rollout_state, spatial, pv.kappa, wp, Ts, B, hio.state, hio.u, hio.flags};
         control_epilogue2<LPS>(cm, mp, w, r, cc, infeas, u_out, iters, qp_status, flags, b, fl, ro);
     };
     admm_solve2<LPS, LOOSE>(cm, s, st, al2, nal2, n, sm, pair_coef_ptr<LPS>(smem_raw, warp, lane), live, emit);
@@ -177,13 +178,13 @@ static void assemble_solve_pair_launch(const MpcParams& mp, const AdmmSettings& 
                                        const double* spatial, const int* wp_id, double* control, const double* ub,
                                        const double* lb, int* infeas, double* u_out, double* x_out, int* iters,
                                        int* qp_status, int* flags, int B, cudaStream_t s, double* rs, double Ts,
-                                       const int* order) {
+                                       const int* order, HostIO hio) {
     constexpr int per_block = kPairWarpsPerBlock * (32 / LPS);
     const size_t smem = pair_smem_bytes<LPS>();
     { static int have_ = 0; ensure_dynamic_smem(assemble_solve_pair_kernel<LPS, LOOSE, kPairMinBlocks>, have_, smem); }
     assemble_solve_pair_kernel<LPS, LOOSE, kPairMinBlocks><<<(B + per_block - 1) / per_block, 32 * kPairWarpsPerBlock, smem, s>>>(
         mp, st, make_float2((float)st.alpha, (float)st.alpha), make_float2(-(float)st.alpha, -(float)st.alpha), pv, spatial, wp_id,
-        control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, rs, Ts, order);
+        control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, rs, Ts, order, hio);
 }
 
 void preload_pair_kernels(int N) {
@@ -208,15 +209,16 @@ int launch_solve_qp_pair(int N, const AdmmSettings& st, const double* Pd, const 
 int launch_assemble_solve_pair(const MpcParams& mp, const AdmmSettings& st, const PathView& pv, const double* spatial,
                                const int* wp_id, double* control, const double* ub, const double* lb, int* infeas,
                                double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B, cudaStream_t s,
-                               double* rollout_state, double Ts, const int* order) {
+                               double* rollout_state, double Ts, const int* order, const HostIO* host_io) {
     NvtxRange nvtx_("mpc:K1+K2 assemble_solve (paired fp32)");
+    const HostIO hio = host_io ? *host_io : HostIO{nullptr, nullptr, nullptr};
     const int ns = mp.N + 1;
     if (ns > 64) return MPC_E_UNSUPPORTED;
     // e_psi and t unbounded (the reference's StateConstraints): OSQP's "loose" rows, skipped by the loop
     const bool loose = mp.xmin[1] <= -kOsqpInfty && mp.xmax[1] >= kOsqpInfty && mp.xmin[2] <= -kOsqpInfty &&
                        mp.xmax[2] >= kOsqpInfty;
-#define PAIR_GO(LPS_) do { if (loose) assemble_solve_pair_launch<LPS_, true>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts, order); \
-                           else assemble_solve_pair_launch<LPS_, false>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts, order); } while (0)
+#define PAIR_GO(LPS_) do { if (loose) assemble_solve_pair_launch<LPS_, true>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts, order, hio); \
+                           else assemble_solve_pair_launch<LPS_, false>(mp, st, pv, spatial, wp_id, control, ub, lb, infeas, u_out, x_out, iters, qp_status, flags, B, s, rollout_state, Ts, order, hio); } while (0)
     if (ns <= 16) PAIR_GO(8); else if (ns <= 32) PAIR_GO(16); else PAIR_GO(32);
 #undef PAIR_GO
     return 0;

@@ -89,6 +89,7 @@ __device__ __forceinline__ void control_epilogue4(const QuadComm<LPS>& cm, const
         if (flags) flags[b] = fl;
         if (iters) iters[b] = r.iters;
         if (qp_status) qp_status[b] = r.status;
+        store_host_results(ro, u_out, b, fl);
     }
 }
 

@@ -93,7 +93,7 @@ __device__ __forceinline__ f2 rho_row(unsigned codes, int sl, int i, float rho, 
 
 template <int LPS> struct QuadFactor {
     static constexpr int NLEV = PairFactor<LPS>::NLEV;
-    int unused;  // the whole factor lives in the HOT columns
+    // no data members: the whole factor lives in the HOT columns (the type only carries NLEV)
 };
 
 __device__ __forceinline__ void inv3sym6p(const f2* M /*00 01 02 11 12 22*/, f2* R) {
@@ -453,7 +453,6 @@ __device__ __forceinline__ void factorize4(const QuadComm<LPS>& cm, const Stage2
     hot[(kHEnd + 1) * 32] = make_float4(last[4], last[5], last[6], last[7]);
     hot[(kHEnd + 2) * 32] = make_float4(last[8], Di[0], Di[1], Di[2]);
     hot[(kHEnd + 3) * 32] = make_float4(Di[4], Di[5], Di[8], 0.0f);
-    (void)f;
     smem_fence();
 }
 

@@ -41,6 +41,7 @@ __device__ __forceinline__ void control_epilogue_tm(const GroupComm<LPS>& cm, co
         if (flags) flags[b] = fl;
         if (iters) iters[b] = r.iters;
         if (qp_status) qp_status[b] = r.status;
+        store_host_results(ro, u_out, b, fl);
     }
 }
 

@@ -710,7 +710,9 @@ static int ensure_width_memo(mpc_engine* h) {
     return 0;
 }
 
-static int enqueue_step(mpc_engine* h, bool with_stats, bool timed, bool stage_hint = false) {
+// `host` (mpc_step_host on page-locked buffers): the caller's state / u / flags as device pointers.  The kernels then read
+// and write the caller's memory themselves and the step needs no copy before or after it.
+static int enqueue_step(mpc_engine* h, bool with_stats, bool timed, bool stage_hint = false, const HostIO* host = nullptr) {
     const int B = h->B;
     cudaStream_t s = h->stream;
     const double sm = h->cfg.car_width / std::sqrt(2.0);
@@ -719,17 +721,22 @@ static int enqueue_step(mpc_engine* h, bool with_stats, bool timed, bool stage_h
     if (!timed) {
         // the solve order is planned by one extra CTA of the raycast launch from the previous step's iteration counts
         int* order = (h->cfg.precision == 0 && B <= (1 << 16) && !h->no_solve_order) ? h->s_order.p : nullptr;
-        if (h->memo_valid && !h->grids_B)
+        HostMirror hm{nullptr, nullptr, nullptr, nullptr};
+        if (host) hm = HostMirror{nullptr, host->flags, h->s_u.p, host->u};
+        if (h->memo_valid && !h->grids_B) {
+            if (host) hm.state_dev_out = h->s_state.p;  // this kernel fetches the state from the caller's memory itself
             launch_localize_gather(h->pv, h->memo_ub.p, h->memo_lb.p, h->memo_flags.p, h->s_wp_id.p, h->cfg.N, h->s_ub.p, h->s_lb.p,
-                                   h->s_flags.p, B, s, h->s_state.p, h->s_wp_id.p, h->s_spatial.p, h->length, h->s_iters.p, order,
-                                   order ? h->d_long : nullptr, h->s_bucket.p);
-        else
+                                   h->s_flags.p, B, s, host ? host->state : h->s_state.p, h->s_wp_id.p, h->s_spatial.p, h->length,
+                                   h->s_iters.p, order, order ? h->d_long : nullptr, h->s_bucket.p, host ? &hm : nullptr);
+        } else {
             launch_raycast(grids, stride, h->g, h->pv, h->d_rowspan.p, h->max_rows, h->d_ray_cells.p, h->d_ray_len.p, h->s_wp_id.p, 1, h->cfg.N, 2 * sm, sm,
                            h->s_ub.p, h->s_lb.p, nullptr, h->s_flags.p, B, h->rowspan_valid, s, h->s_state.p, h->s_wp_id.p,
-                           h->s_spatial.p, h->length, h->s_iters.p, order, order ? h->d_long : nullptr, h->s_bucket.p);
+                           h->s_spatial.p, h->length, h->s_iters.p, order, order ? h->d_long : nullptr, h->s_bucket.p,
+                           host ? &hm : nullptr);
+        }
         int r = launch_assemble_solve(h->cfg.precision, h->mp, h->st, h->pv, h->s_spatial.p, h->s_wp_id.p, h->s_control.p,
                                       h->s_ub.p, h->s_lb.p, h->s_infeas.p, h->s_u.p, nullptr, h->s_iters.p,
-                                      h->s_qp_status.p, h->s_flags.p, B, s, h->s_state.p, h->cfg.Ts, order, stage_hint);
+                                      h->s_qp_status.p, h->s_flags.p, B, s, h->s_state.p, h->cfg.Ts, order, stage_hint, host);
         if (r) return fail(r, "unsupported horizon");
         // the rollout only touches `state`; flags / iters / e_y of this step are final, so the statistics can follow it
         if (with_stats) launch_accumulate_stats(h->s_flags.p, h->s_iters.p, h->s_spatial.p, h->s_acc.p, B, s);
@@ -902,7 +909,24 @@ static bool host_pinned(mpc_engine* h, int slot, const void* p, size_t bytes) {
     return true;
 }
 
-// H2D state -> localise+raycast -> assemble+solve+rollout -> D2H (state, u, flags): one graph, one launch
+// the caller's page-locked buffers as the device sees them; false if any of them is not mapped into the device's space
+static bool host_device_pointers(double* h_state, double* h_u_out, int32_t* h_flags, HostIO* out) {
+    void *ds = nullptr, *du = nullptr, *df = nullptr;
+    if (cudaHostGetDevicePointer(&ds, h_state, 0) != cudaSuccess || cudaHostGetDevicePointer(&du, h_u_out, 0) != cudaSuccess ||
+        (h_flags && cudaHostGetDevicePointer(&df, h_flags, 0) != cudaSuccess)) {
+        cudaGetLastError();
+        return false;
+    }
+    *out = HostIO{static_cast<double*>(ds), static_cast<double*>(du), static_cast<int*>(df)};
+    return true;
+}
+
+// One graph, one launch per step on page-locked caller buffers.  Default: NO copy nodes -- the first kernel reads the state
+// from the caller's memory (coalesced, localize_gather_kernel) and the solve kernel's epilogue stores new state, control
+// and flags there (admm_epilogue.cuh: store_host_results); scenarios the step skips are covered by the first kernel.  With
+// per-scenario grids the ray-cast kernel keeps its device-side state, so that path has one H2D node in front.
+// MPC_HOST_IO=copy, or a solve kernel without the host epilogue (MPC_ADMM_KERNEL=tm / quad), selects the graph
+// H2D state -> kernels -> D2H (state, u, flags).
 static int ensure_io_graph(mpc_engine* h, double* h_state, double* h_u_out, int32_t* h_flags) {
     if (h->io_graph[0] && h->io_graph[1] && h->io_B == h->B && h->io_key[0] == h_state && h->io_key[1] == h_u_out &&
         h->io_key[2] == h_flags)
@@ -913,6 +937,11 @@ static int ensure_io_graph(mpc_engine* h, double* h_state, double* h_u_out, int3
     }
     const size_t B = h->B;
     if (int r0 = ensure_width_memo(h)) return r0;  // before the capture: it synchronises
+    const char* io_env = getenv("MPC_HOST_IO");
+    HostIO mapped{nullptr, nullptr, nullptr};
+    const bool zero_copy = !(io_env && io_env[0] == 'c') && solve_writes_host_io() &&
+                           host_device_pointers(h_state, h_u_out, h_flags, &mapped);
+    const bool kernel_reads_host = zero_copy && h->memo_valid && !h->grids_B;
     cudaStream_t cap = h->stream, own = nullptr;
     if (cap == nullptr) {
         CUDA_OK(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
@@ -928,10 +957,11 @@ static int ensure_io_graph(mpc_engine* h, double* h_state, double* h_u_out, int3
         e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
         if (e != cudaSuccess) break;
         const int64_t l0 = h->launches;
-        cudaMemcpyAsync(h->s_state.p, h_state, 4 * B * sizeof(double), cudaMemcpyHostToDevice, cap);
-        r = enqueue_step(h, false, false, v == 1);
+        if (!kernel_reads_host) cudaMemcpyAsync(h->s_state.p, h_state, 4 * B * sizeof(double), cudaMemcpyHostToDevice, cap);
+        r = enqueue_step(h, false, false, v == 1, zero_copy ? &mapped : nullptr);
         h->launches = l0;
-        if (one_block) {  // the caller's buffers are laid out like s_io (mpc_host_io): one copy
+        if (zero_copy) {
+        } else if (one_block) {  // the caller's buffers are laid out like s_io (mpc_host_io): one copy
             cudaMemcpyAsync(h_state, h->s_io.p, 6 * B * sizeof(double) + (h_flags ? B * sizeof(int) : 0), cudaMemcpyDeviceToHost, cap);
         } else {
             cudaMemcpyAsync(h_state, h->s_state.p, 4 * B * sizeof(double), cudaMemcpyDeviceToHost, cap);

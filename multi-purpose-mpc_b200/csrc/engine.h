@@ -8,6 +8,22 @@
 
 namespace mpcb {
 
+struct HostIO {  // mpc_step_host: the caller's page-locked buffers as device pointers (all null = off)
+    double* state;
+    double* u;
+    int* flags;
+};
+
+// mpc_step_host on page-locked buffers without copy nodes: what the first kernel of the step does on the caller's
+// (device-mapped) host memory.  The solve kernel's epilogue writes the results of every scenario it solves (HostIO); the
+// first kernel covers the ones it skips or retires.
+struct HostMirror {
+    double* state_dev_out;  // device copy of the state read from the host (localize_gather_kernel only), or null
+    int* flags_host;        // scenarios skipped / retired by this kernel: flags ...
+    const double* u_dev;    // ... and the control the device holds for them
+    double* u_host;
+};
+
 struct GridView {
     int H, W, pitch_words;  // row pitch in 32-bit words (multiple of 16 -> 64 B)
     double ox, oy, res;
@@ -30,12 +46,14 @@ void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridV
                     double sm, double* ub, double* lb, double* cells_sm, int* flags, int B, bool rowspan_ok,
                     cudaStream_t st, const double* state = nullptr, int* wp_id_out = nullptr,
                     double* spatial_out = nullptr, double length = 0.0, const int* prev_iters = nullptr,
-                    int* order_out = nullptr, int* long_out = nullptr, unsigned char* bucket_of = nullptr);
+                    int* order_out = nullptr, int* long_out = nullptr, unsigned char* bucket_of = nullptr,
+                    const HostMirror* mirror = nullptr);
 void launch_localize_gather(const PathView& pv, const double* memo_ub, const double* memo_lb, const int* memo_flags,
                             const int* wp_id, int N, double* ub, double* lb, int* flags, int B, cudaStream_t st,
                             const double* state = nullptr, int* wp_id_out = nullptr, double* spatial_out = nullptr,
                             double length = 0.0, const int* prev_iters = nullptr, int* order_out = nullptr,
-                            int* long_out = nullptr, unsigned char* bucket_of = nullptr);
+                            int* long_out = nullptr, unsigned char* bucket_of = nullptr,
+                            const HostMirror* mirror = nullptr);
 void launch_localize(const double* state, int* wp_id, double* spatial, int* flags, const PathView& pv, double length,
                      int B, cudaStream_t st);
 void launch_rollout(double* state, const double* spatial, const int* wp_id, const double* u, const int* flags,
@@ -51,8 +69,9 @@ int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings
                           const double* spatial, const int* wp_id, double* control, const double* ub, const double* lb,
                           int* infeas, double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B,
                           cudaStream_t s, double* rollout_state = nullptr, double Ts = 0.0, const int* order = nullptr,
-                          bool prefer_stage = false);
+                          bool prefer_stage = false, const HostIO* host_io = nullptr);
 
+bool solve_writes_host_io();  // false for the opt-in variants (MPC_ADMM_KERNEL=tm / quad), which only fill device buffers
 void preload_solve_kernels(int precision, int N, int B = 0);
 void preload_pair_kernels(int N);
 void preload_quad_kernels(int N);
@@ -73,6 +92,6 @@ int launch_solve_qp_pair(int N, const AdmmSettings& st, const double* Pd, const 
 int launch_assemble_solve_pair(const MpcParams& mp, const AdmmSettings& st, const PathView& pv, const double* spatial,
                                const int* wp_id, double* control, const double* ub, const double* lb, int* infeas,
                                double* u_out, double* x_out, int* iters, int* qp_status, int* flags, int B, cudaStream_t s,
-                               double* rollout_state, double Ts, const int* order);
+                               double* rollout_state, double Ts, const int* order, const HostIO* host_io = nullptr);
 
 }  // namespace mpcb

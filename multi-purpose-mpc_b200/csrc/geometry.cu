@@ -202,9 +202,8 @@ __device__ __forceinline__ int localize_one(const double* __restrict__ state, do
 // The same for a whole warp working on one car: the search over the cumulative lengths is spread over the lanes
 // (independent loads instead of a chain of dependent ones; length_cum is non-decreasing, so the first index with
 // length_cum > s is the number of entries <= s).  Returns the waypoint in every lane; lane 0 writes `spatial`.
-__device__ __forceinline__ int localize_warp(const double* __restrict__ state, double* __restrict__ spatial,
-                                             const PathView& pv, double length, int b, int B, int lane) {
-    const double s = state[3 * (size_t)B + b];
+__device__ __forceinline__ int localize_warp_values(double x, double y, double psi, double s, double* __restrict__ spatial,
+                                                    const PathView& pv, double length, int b, int B, int lane) {
     int cnt = 0;
     for (int i = lane; i < pv.n_wp; i += 32) cnt += (pv.length_cum[i] > s) ? 0 : 1;
     const int lo = __reduce_add_sync(0xffffffffu, cnt);
@@ -212,7 +211,6 @@ __device__ __forceinline__ int localize_warp(const double* __restrict__ state, d
     const int next = lo, prev = next > 0 ? next - 1 : pv.n_wp - 1;  // index -1 wraps in numpy
     int w = 0;
     if (lane == 0) {
-        const double x = state[b], y = state[(size_t)B + b], psi = state[2 * (size_t)B + b];
         const double s_next = pv.length_cum[next], s_prev = pv.length_cum[prev];
         w = (fabs(s - s_next) < fabs(s - s_prev)) ? next : prev;  // strict <: ties -> prev (quirk Q8)
         const double e_y = pv.cos_psi[w] * (y - pv.y[w]) - pv.sin_psi[w] * (x - pv.x[w]);  // sbm.py:202-205
@@ -223,6 +221,13 @@ __device__ __forceinline__ int localize_warp(const double* __restrict__ state, d
         spatial[(size_t)B + b] = e_psi;
     }
     return __shfl_sync(0xffffffffu, w, 0);
+}
+__device__ __forceinline__ int localize_warp(const double* __restrict__ state, double* __restrict__ spatial,
+                                             const PathView& pv, double length, int b, int B, int lane) {
+    const double s = state[3 * (size_t)B + b];
+    double x = 0.0, y = 0.0, psi = 0.0;  // used by lane 0 only
+    if (lane == 0) { x = state[b]; y = state[(size_t)B + b]; psi = state[2 * (size_t)B + b]; }
+    return localize_warp_values(x, y, psi, s, spatial, pv, length, b, B, lane);
 }
 
 __global__ void localize_t2s_kernel(const double* __restrict__ state, int* __restrict__ wp_id,
@@ -536,7 +541,24 @@ struct RaycastArgs {
     int* order_out;
     int* long_out;  // host-mapped: number of live scenarios whose previous solve took >= kLongSolve iterations
     unsigned char* bucket_of;  // [B] scratch of the planner CTA (see plan_solve_order)
+    // mpc_step_host on page-locked buffers: `state` then points into the CALLER's host memory (device-mapped); the kernel
+    // leaves a device copy for the solve kernel's rollout and mirrors the flags it sets into the caller's flags
+    HostMirror hm;
 };
+
+// lane 0: scenario b does not reach the solve kernel this step -- hand the caller its flags and the control on record
+__device__ __forceinline__ void mirror_skipped(const RaycastArgs& a, int b, int fl) {
+    if (a.hm.flags_host) a.hm.flags_host[b] = fl;
+    if (a.hm.u_host) {
+        a.hm.u_host[2 * (size_t)b] = a.hm.u_dev[2 * (size_t)b];
+        a.hm.u_host[2 * (size_t)b + 1] = a.hm.u_dev[2 * (size_t)b + 1];
+    }
+}
+__device__ __forceinline__ void flag_scenario(const RaycastArgs& a, int b, int bits) {  // lane 0
+    if (!a.flags) return;
+    const int old = atomicOr(&a.flags[b], bits);
+    mirror_skipped(a, b, old | bits);
+}
 
 // Solve order for the paired ADMM kernel.  Its warps hold 2-4 scenarios that run in lockstep until the slowest is
 // done, and CTAs are dispatched in index order; the iteration count of a car's previous solve predicts the next one
@@ -652,12 +674,15 @@ raycast_kernel(RaycastArgs a) {
     uint32_t phase = 0;
     for (int b = blockIdx.x * nwarps + warp; b < a.B; b += ray_ctas * nwarps) {
         const int fl = a.flags ? a.flags[b] : 0;
-        if (fl & (MPC_ST_DEAD | MPC_ST_FINISHED)) continue;
+        if (fl & (MPC_ST_DEAD | MPC_ST_FINISHED)) {
+            if (lane == 0) mirror_skipped(a, b, fl);
+            continue;
+        }
         int wp_now;
         if (a.state) {  // get_current_waypoint + t2s (sbm.py:256-279, 183-219), same arithmetic as localize_t2s_kernel
             const int w = localize_warp(a.state, a.spatial_out, pv, a.length, b, a.B, lane);
             if (w < 0) {
-                if (lane == 0 && a.flags) atomicOr(&a.flags[b], MPC_ST_FINISHED);
+                if (lane == 0) flag_scenario(a, b, MPC_ST_FINISHED);
                 continue;
             }
             if (lane == 0) a.wp_id_out[b] = w;
@@ -700,7 +725,7 @@ raycast_kernel(RaycastArgs a) {
         if (nsegs[0] == 0) status |= MPC_ST_NO_SEGMENT;  // rp.py:547 max([]) -> ValueError
         status = __reduce_or_sync(0xffffffffu, status);
         if (status) {
-            if (lane == 0 && a.flags) atomicOr(&a.flags[b], status | MPC_ST_DEAD);
+            if (lane == 0) flag_scenario(a, b, status | MPC_ST_DEAD);
             continue;
         }
         double* ub_o = a.ub_out + (size_t)b * N;
@@ -819,14 +844,40 @@ localize_gather_kernel(RaycastArgs a, const double* __restrict__ memo_ub, const 
         plan_solve_order(a.prev_iters, a.flags, a.order_out, a.long_out, a.bucket_of, a.B);
         return;
     }
-    for (int b = blockIdx.x * nwarps + warp; b < a.B; b += ray_ctas * nwarps) {
+    // With the caller's page-locked state as input (hm.state_dev_out set) the 32 scenarios of one round of the CTA are
+    // fetched over PCIe by 128 threads as four coalesced 256 B reads, left in HBM for the solve kernel's rollout, and
+    // handed to the warps through shared memory (two buffers: one barrier per round).
+    __shared__ double staged[2][4][32];
+    const bool from_host = a.state && a.hm.state_dev_out;
+    int round = 0;
+    for (int base = blockIdx.x * nwarps; base < a.B; base += ray_ctas * nwarps, ++round) {  // CTA-uniform trip count
+        const int b = base + warp;
+        if (from_host) {
+            const int k = threadIdx.x / nwarps, j = threadIdx.x - k * nwarps;
+            if (k < 4 && base + j < a.B) {
+                const double v = a.state[(size_t)k * a.B + base + j];
+                staged[round & 1][k][j] = v;
+                a.hm.state_dev_out[(size_t)k * a.B + base + j] = v;
+            }
+            __syncthreads();
+        }
+        if (b >= a.B) continue;
         const int fl = a.flags ? a.flags[b] : 0;
-        if (fl & (MPC_ST_DEAD | MPC_ST_FINISHED)) continue;
+        if (fl & (MPC_ST_DEAD | MPC_ST_FINISHED)) {
+            if (lane == 0) mirror_skipped(a, b, fl);
+            continue;
+        }
         int w;
         if (a.state) {
-            w = localize_warp(a.state, a.spatial_out, pv, a.length, b, a.B, lane);
+            if (from_host) {
+                const double(*sv)[32] = staged[round & 1];
+                w = localize_warp_values(sv[0][warp], sv[1][warp], sv[2][warp], sv[3][warp], a.spatial_out, pv, a.length, b,
+                                         a.B, lane);
+            } else {
+                w = localize_warp(a.state, a.spatial_out, pv, a.length, b, a.B, lane);
+            }
             if (w < 0) {
-                if (lane == 0 && a.flags) atomicOr(&a.flags[b], MPC_ST_FINISHED);
+                if (lane == 0) flag_scenario(a, b, MPC_ST_FINISHED);
                 continue;
             }
             if (lane == 0) a.wp_id_out[b] = w;
@@ -835,7 +886,7 @@ localize_gather_kernel(RaycastArgs a, const double* __restrict__ memo_ub, const 
         }
         const int st = memo_flags[w];  // what the ray-cast of this horizon reported (incl. MPC_ST_DEAD), 0 = fine
         if (st) {
-            if (lane == 0 && a.flags) atomicOr(&a.flags[b], st);
+            if (lane == 0) flag_scenario(a, b, st);
             continue;
         }
         for (int n = lane; n < N; n += 32) {
@@ -848,9 +899,10 @@ localize_gather_kernel(RaycastArgs a, const double* __restrict__ memo_ub, const 
 void launch_localize_gather(const PathView& pv, const double* memo_ub, const double* memo_lb, const int* memo_flags,
                             const int* wp_id, int N, double* ub, double* lb, int* flags, int B, cudaStream_t st,
                             const double* state, int* wp_id_out, double* spatial_out, double length, const int* prev_iters,
-                            int* order_out, int* long_out, unsigned char* bucket_of) {
+                            int* order_out, int* long_out, unsigned char* bucket_of, const HostMirror* mirror) {
     NvtxRange nvtx_("mpc:K4a+K3 localize + width-table replay");
     RaycastArgs a{};
+    if (mirror) a.hm = *mirror;
     a.prev_iters = prev_iters; a.order_out = (order_out && bucket_of) ? order_out : nullptr; a.long_out = long_out; a.bucket_of = bucket_of;
     a.state = state; a.wp_id_out = wp_id_out; a.spatial_out = spatial_out; a.length = length;
     a.pv = pv; a.wp_id = wp_id; a.first_offset = 1; a.N = N; a.ub_out = ub; a.lb_out = lb; a.flags = flags; a.B = B;
@@ -917,9 +969,11 @@ void launch_raycast(const uint32_t* grids, size_t grid_stride_words, const GridV
                     const int2* rowspan, int max_rows, const uint32_t* ray_cells, const int* ray_len, const int* wp_id, int first_offset, int N, double min_width,
                     double sm, double* ub, double* lb, double* cells_sm, int* flags, int B, bool rowspan_ok,
                     cudaStream_t st, const double* state, int* wp_id_out, double* spatial_out, double length,
-                    const int* prev_iters, int* order_out, int* long_out, unsigned char* bucket_of) {
+                    const int* prev_iters, int* order_out, int* long_out, unsigned char* bucket_of,
+                    const HostMirror* mirror) {
     NvtxRange nvtx_("mpc:K3 raycast");
     RaycastArgs a;
+    a.hm = mirror ? *mirror : HostMirror{nullptr, nullptr, nullptr, nullptr};
     a.prev_iters = prev_iters; a.order_out = (order_out && bucket_of) ? order_out : nullptr; a.long_out = long_out; a.bucket_of = bucket_of;
     a.state = state; a.wp_id_out = wp_id_out; a.spatial_out = spatial_out; a.length = length;
     a.grids = grids; a.grid_stride_words = grid_stride_words; a.g = g; a.pv = pv; a.rowspan = rowspan; a.wp_id = wp_id;

@@ -345,6 +345,66 @@ def test_closed_loop_graph_equals_stepwise(engine_factory):
     assert np.array_equal(ts.numpy(), oa["state"]) and np.array_equal(tu.numpy(), oa["u"])
 
 
+@pytest.mark.parametrize("per_scenario_grids", [False, True])
+@pytest.mark.parametrize("precision", [0, 1])
+def test_host_step_without_copy_nodes(engine_factory, track, monkeypatch, per_scenario_grids, precision):
+    """mpc_step_host on page-locked buffers: the kernels read / write the caller's memory themselves (no copy nodes in the
+    graph).  Same bits as device-resident stepping and as the H2D -> kernels -> D2H graph (MPC_HOST_IO=copy), with
+    scenarios that are blocked, run out of path, or were finished before the first step in the batch, and with flags
+    omitted."""
+    import mpc_b200
+    TF = load_golden("teacher_forced.npz")
+    B = 203                                                      # not a multiple of the 32 scenarios a CTA stages per round
+    rng = np.random.default_rng(5)
+    st0 = np.ascontiguousarray(TF["state"][rng.integers(0, TF["state"].shape[0], B)].T)
+    st0[0] += rng.uniform(-0.002, 0.002, B)
+    st0[3, 7] = track.length + 0.01                              # finished before the first step
+    st0[3, 100] = track.length - 0.05                            # horizon runs over the end of the path
+    w = int(TF["wp_id"][0])
+    blk = (w + 1) % track.n_wp
+    obs = np.array([[track.wp_x[blk], track.wp_y[blk], 0.3]])
+    off = np.zeros(B + 1, np.int32); off[4:] = 1                 # scenario 3 is blocked
+    st0[:, 3] = TF["state"][0]
+
+    def make():
+        e = engine_factory(grid="free", precision=precision)
+        if per_scenario_grids:
+            e.set_obstacles(obs, off)
+        e.scenarios_init(st0)
+        return e
+
+    steps = 6
+    dev = make()
+    for _ in range(steps):
+        dev.step()
+    od = dev.scenarios_read()
+    if per_scenario_grids:
+        assert od["flags"][3] & mpc_b200.ST_DEAD
+    assert od["flags"][7] & mpc_b200.ST_FINISHED and od["flags"][100] != 0
+
+    def run_host(with_flags):
+        e = make()
+        hs, hu, hf = e.host_io()
+        hs[:] = st0
+        hu[:] = 0.0
+        hf[:] = -1
+        for _ in range(steps):
+            e.step_host(hs, hu, hf if with_flags else None)
+        o = e.scenarios_read()
+        return hs.copy(), hu.copy(), hf.copy(), o
+
+    for mode in ("kernel", "copy"):
+        monkeypatch.setenv("MPC_HOST_IO", mode)
+        for with_flags in (True, False):
+            hs, hu, hf, o = run_host(with_flags)
+            assert np.array_equal(hs, od["state"]), (mode, with_flags)
+            assert np.array_equal(hu, od["u"]), (mode, with_flags)
+            if with_flags:
+                assert np.array_equal(hf, od["flags"]), mode
+            for k in ("state", "u", "flags", "iters", "wp_id"):   # and the device copies stay in step with the caller's
+                assert np.array_equal(o[k], od[k]), (mode, k)
+
+
 def test_batch_properties_at_c2_size(engine_factory, track):
     """BASELINE config 2 size (4096 cars): permutation equivariance and replica consistency of a full step."""
     from mpc_b200 import distributed as D
