@@ -201,13 +201,15 @@ int mpc_scenarios_set_state(mpc_engine *h, const double *h_state, const double *
 int mpc_scenarios_set_flags(mpc_engine *h, const int32_t *h_flags);
 int mpc_step(mpc_engine *h);
 int mpc_run_closed_loop(mpc_engine *h, int32_t max_steps, double *h_stats);
-/* host-buffer variant of one step (the e2e path): H2D of h_state[4][B], step, D2H of h_u_out[B][2]
- * and the new h_state.  Synchronous. */
+/* host-buffer variant of one step (the e2e path): reads h_state[4][B], steps, leaves h_u_out[B][2], the new h_state
+ * and (optionally) h_flags[B] in the caller's memory.  Synchronous. */
 int mpc_step_host(mpc_engine *h, double *h_state, double *h_u_out, int32_t *h_flags);
 /* mpc_step_host copies through an internal page-locked block when the caller's buffers are pageable.  When
  * they are page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory, or the engine's own block
- * returned here: state[4][B] | u[B][2] | flags[B], valid until the next mpc_scenarios_init) the DMA engines
- * address them directly and the whole step -- H2D, the two kernels, D2H -- is one CUDA-graph launch. */
+ * returned here: state[4][B] | u[B][2] | flags[B], valid until the next mpc_scenarios_init) the step is one
+ * CUDA-graph launch with no copies at all: the first kernel reads the state out of the caller's memory and the
+ * solve kernel stores its results there (environment MPC_HOST_IO=copy: H2D node + kernels + D2H node instead;
+ * same bits either way). */
 int mpc_host_io(mpc_engine *h, double **h_state, double **h_u, int32_t **h_flags);
 /* device views of the engine-owned scenario arrays (for zero-copy inspection from torch/ctypes) */
 int mpc_scenarios_ptrs(mpc_engine *h, double **d_state, double **d_spatial, int32_t **d_wp_id,

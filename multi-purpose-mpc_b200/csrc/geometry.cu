@@ -579,14 +579,36 @@ __device__ void plan_solve_order(const int* __restrict__ prev_iters, const int* 
     // value, never the flags, so histogram and cursors always describe the same assignment and `order` is a permutation
     // of 0..B-1.  A scenario that finishes during this launch merely keeps an early slot; the solve kernel re-reads its
     // flags and skips it.
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        int k = NB - 1;  // skipped by the solve: last
-        if (!(flags && (flags[b] & (MPC_ST_DEAD | MPC_ST_FINISHED)))) {
-            const int q = prev_iters[b] / 25;
-            k = NB - 1 - (q < 0 ? 0 : (q < NB - 1 ? q : NB - 1));
+    // Most scenarios of a step share two or three buckets, so per-lane shared-memory atomics would serialise on those
+    // addresses.  Lanes with the same bucket are grouped with match.any and one of them adds the group's size: a handful
+    // of atomics per warp.
+    // The loads of four rounds are issued together: the CTA is on the step's critical path and would otherwise pay one
+    // global-memory latency per round and operand.
+    const int lane = threadIdx.x & 31;
+    constexpr int U = 4;
+    for (int b0 = threadIdx.x - lane; b0 < B; b0 += U * blockDim.x) {  // warp-uniform trip count
+        int fl[U], it[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int b = b0 + u * blockDim.x + lane;
+            fl[u] = (b < B && flags) ? flags[b] : 0;
+            it[u] = b < B ? prev_iters[b] : 0;
         }
-        bucket_of[b] = (unsigned char)k;
-        atomicAdd(&hist[k], 1);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int b = b0 + u * blockDim.x + lane;
+            int k = -1;
+            if (b < B) {
+                k = NB - 1;  // skipped by the solve: last
+                if (!(fl[u] & (MPC_ST_DEAD | MPC_ST_FINISHED))) {
+                    const int q = it[u] / 25;
+                    k = NB - 1 - (q < 0 ? 0 : (q < NB - 1 ? q : NB - 1));
+                }
+                bucket_of[b] = (unsigned char)k;
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, k);
+            if (k >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[k], __popc(peers));
+        }
     }
     __syncthreads();
     __shared__ int wsum[NB / 32], nlong_s;
@@ -594,7 +616,7 @@ __device__ void plan_solve_order(const int* __restrict__ prev_iters, const int* 
     if (blockDim.x >= NB) {
         // exclusive scan of the histogram by the first six warps (NB = 192 = 6 x 32 lanes): warp scan + carry
         if (threadIdx.x < NB) {
-            const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+            const int w = threadIdx.x >> 5;
             int v = hist[threadIdx.x];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -623,9 +645,24 @@ __device__ void plan_solve_order(const int* __restrict__ prev_iters, const int* 
     __syncthreads();
     // feeds the host's choice between the paired and the lane-per-stage solve kernel for a LATER step (engine.cu)
     if (threadIdx.x == 0 && long_out) *long_out = nlong_s;
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        const int slot = atomicAdd(&cursor[bucket_of[b]], 1);
-        if (slot < B) order[slot] = b;  // always true for a consistent histogram; never write past the array
+    for (int b0 = threadIdx.x - lane; b0 < B; b0 += U * blockDim.x) {
+        int kk[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int b = b0 + u * blockDim.x + lane;
+            kk[u] = b < B ? (int)bucket_of[b] : -1;  // written by this very thread in the histogram pass
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int b = b0 + u * blockDim.x + lane, k = kk[u];
+            const unsigned peers = __match_any_sync(0xffffffffu, k);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (k >= 0 && lane == leader) base = atomicAdd(&cursor[k], __popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            const int slot = base + __popc(peers & ((1u << lane) - 1u));
+            if (k >= 0 && slot < B) order[slot] = b;  // always true for a consistent histogram; never write past the array
+        }
     }
 }
 
