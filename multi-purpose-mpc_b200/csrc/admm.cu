@@ -298,6 +298,19 @@ int launch_solve_qp(int precision, int N, const AdmmSettings& st, const double* 
     return 0;
 }
 
+// K1's per-waypoint coefficients (PathView::stage_tab), rebuilt whenever the path, v_ref or R change
+__global__ void stage_table_kernel(PathView pv, double R0, double R1, double* __restrict__ tab) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= pv.n_wp) return;
+    double o[kStageTab];
+    stage_coefficients(pv.ds_next[w], pv.kappa[w], pv.v_ref[w], R0, R1, o);
+#pragma unroll
+    for (int i = 0; i < kStageTab; ++i) tab[(size_t)w * kStageTab + i] = o[i];
+}
+void launch_build_stage_table(const PathView& pv, const MpcParams& mp, double* tab, cudaStream_t s) {
+    stage_table_kernel<<<(pv.n_wp + 127) / 128, 128, 0, s>>>(pv, mp.R[0], mp.R[1], tab);
+}
+
 bool solve_writes_host_io() { return !(use_tm_kernel() || use_quad_kernel()); }
 
 int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings& st, const PathView& pv,

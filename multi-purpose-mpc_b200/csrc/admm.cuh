@@ -47,7 +47,24 @@ struct PathView {  // device tables, one row per quantity (set by mpc_set_path)
     const double *x, *y, *psi, *kappa, *v_ref, *ds_next, *cos_psi, *sin_psi, *cos_ub, *sin_ub, *cos_lb, *sin_lb;
     const double *length_cum;
     const double *border;  // [n_wp][4]
+    // [n_wp][kStageTab]: what K1 needs per waypoint and what depends on the path, v_ref and R only -- the entries of A_lin,
+    // B_lin, uq and q of MPC.py:96-108,125-131 -- evaluated once in fp64 by stage_table_kernel (admm.cu) instead of twice
+    // per lane in front of every solve (four fp64 divisions per stage on the critical path of the solve kernel)
+    const double *stage_tab;
 };
+// row of PathView::stage_tab for waypoint w:  ds | -(kappa^2) ds | -kappa / v_ref ds | -1 / v_ref^2 ds | -R0 v_ref | -R1 kappa
+// | ds kappa | (-1 / v_ref^2 ds) v_ref - (1 / v_ref ds)
+constexpr int kStageTab = 8;
+__host__ __device__ __forceinline__ void stage_coefficients(double ds, double kap, double vr, double R0, double R1, double* o) {
+    o[0] = ds;
+    o[1] = -(kap * kap) * ds;               // A_lin[1][0]   sbm.py:404
+    o[2] = -kap / vr * ds;                  // A_lin[2][0]   sbm.py:406
+    o[3] = -1 / (vr * vr) * ds;             // B_lin[2][0]   sbm.py:410
+    o[4] = -R0 * vr;                        // q of v        MPC.py:129-131
+    o[5] = -R1 * kap;                       // q of kappa
+    o[6] = ds * kap;                        // uq[1] = B_lin[1][1] kappa_ref            MPC.py:107-108
+    o[7] = (-1 / (vr * vr) * ds) * vr - (1 / vr * ds);  // uq[2] = B_lin[2][0] v_ref - f[2]
+}
 
 // ------------------------------------------------------------------------------------------------
 // neighbour exchange + reductions between the stages of one scenario
@@ -771,13 +788,14 @@ __device__ __forceinline__ void assemble_stage(Stage<T>& s, const MpcParams& mp,
     if (k < N) {
         int w0 = wp_id + k;
         if (w0 >= pv.n_wp) w0 %= pv.n_wp;  // rp.py:364-365 (non-circular end-of-path is flagged by the caller)
-        const double ds = pv.ds_next[w0], kap = pv.kappa[w0], vr = pv.v_ref[w0];
-        s.a[0] = T(1); s.a[1] = T(ds);
-        s.a[2] = T(-(kap * kap) * ds); s.a[3] = T(1); s.a[6] = T(ds);
-        s.a[4] = T(-kap / vr * ds); s.a[5] = T(1); s.a[7] = T(-1 / (vr * vr) * ds);
+        const double2* row = reinterpret_cast<const double2*>(pv.stage_tab) + (size_t)w0 * (kStageTab / 2);
+        const double2 t01 = row[0], t23 = row[1], t45 = row[2];
+        s.a[0] = T(1); s.a[1] = T(t01.x);
+        s.a[2] = T(t01.y); s.a[3] = T(1); s.a[6] = T(t01.x);
+        s.a[4] = T(t23.x); s.a[5] = T(1); s.a[7] = T(t23.y);
         s.e[3] = T(1); s.e[4] = T(1);
         s.P[0] = T(mp.Q[0]); s.P[1] = T(mp.Q[1]); s.P[2] = T(mp.Q[2]); s.P[3] = T(mp.R[0]); s.P[4] = T(mp.R[1]);
-        s.q[3] = T(-mp.R[0] * vr); s.q[4] = T(-mp.R[1] * kap);
+        s.q[3] = T(t45.x); s.q[4] = T(t45.y);
         // input bounds; speed limit from predicted curvature (MPC.py:86-87,111-113; quirk Q1)
         const double kp = tan(cc[3 + k] + cc[2 * N - 1]) / mp.L;
         const double vmax_dyn = sqrt(mp.ay_max / (fabs(kp) + 1e-12));
@@ -793,11 +811,11 @@ __device__ __forceinline__ void assemble_stage(Stage<T>& s, const MpcParams& mp,
     } else {
         int wm = wp_id + k - 1;
         if (wm >= pv.n_wp) wm %= pv.n_wp;
-        const double ds = pv.ds_next[wm], kap = pv.kappa[wm], vr = pv.v_ref[wm];
         // uq = B_lin.dot([v_ref, kappa_ref]) - f  (MPC.py:107-108)
+        const double2 t67 = reinterpret_cast<const double2*>(pv.stage_tab)[(size_t)wm * (kStageTab / 2) + 3];
         s.d[0] = T(0);
-        s.d[1] = T(ds * kap);
-        s.d[2] = T((-1 / (vr * vr) * ds) * vr - (1 / vr * ds));
+        s.d[1] = T(t67.x);
+        s.d[2] = T(t67.y);
         const double l_ = lb[k - 1], u_ = ub[k - 1];
         s.lo[0] = T(clip_inf(l_)); s.hi[0] = T(clip_inf(u_));
         const double xr = (l_ + u_) / 2;  // MPC.py:125

@@ -126,6 +126,7 @@ assemble_solve_pair_kernel(MpcParams mp, AdmmSettings st, const f2 al2, const f2
                            int* __restrict__ flags, int B, double* __restrict__ rollout_state, double Ts,
                            const int* __restrict__ order, HostIO hio) {
     constexpr int G = 32 / LPS;
+    MPC_PHASE_MARK(0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = (blockIdx.x * kPairWarpsPerBlock + warp) * G + lane / LPS;
     // `order` (closed-loop path): scenarios sorted by the length of their previous solve, see geometry.cu::plan_solve_order
@@ -157,6 +158,14 @@ assemble_solve_pair_kernel(MpcParams mp, AdmmSettings st, const f2 al2, const f2
         control_epilogue2<LPS>(cm, mp, w, r, cc, infeas, u_out, iters, qp_status, flags, b, fl, ro);
     };
     admm_solve2<LPS, LOOSE>(cm, s, st, al2, nal2, n, sm, pair_coef_ptr<LPS>(smem_raw, warp, lane), live, emit);
+#ifdef MPC_PHASE_CLOCK
+    MPC_PHASE_MARK(6);
+    if (lane == 0 && (blockIdx.x & 127) == 0) {
+        const long long* t = phase_clock_buf();
+        printf("cta %4d  assemble %6lld  scale %6lld  factorise %6lld  pass1 %6lld  to-first-result %7lld  emit %6lld  rest %7lld\n",
+               (int)blockIdx.x, t[1] - t[0], t[2] - t[1], t[3] - t[2], t[7] - t[3], t[4] - t[3], t[5] - t[4], t[6] - t[5]);
+    }
+#endif
 }
 
 constexpr int kPairMinBlocks = 8;

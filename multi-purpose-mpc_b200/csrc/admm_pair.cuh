@@ -543,6 +543,15 @@ __device__ __forceinline__ void set_rho2(const f2* sm, int gl, float rho, float&
 // from pass to pass):   56..60 alpha D (dx) | 61..63 dy of the dynamics rows | 64..68 dy of the bound rows
 constexpr int kPairRows = 69;
 
+// -DMPC_PHASE_CLOCK: a diagnostic build in which lane 0 of every 128th CTA prints the SM clock at the phase boundaries of
+// its solve (kernel entry, assembled, scaled, factorised, first result emitted, loop left).  One warp per CTA assumed.
+#ifdef MPC_PHASE_CLOCK
+__device__ __forceinline__ long long* phase_clock_buf() { __shared__ long long t[8]; return t; }
+#define MPC_PHASE_MARK(k) do { if ((threadIdx.x & 31) == 0) phase_clock_buf()[k] = clock64(); } while (0)
+#else
+#define MPC_PHASE_MARK(k) do { } while (0)
+#endif
+
 // The OSQP loop.  ALL lanes of the warp call this together (every group = one scenario).  Control flow around
 // the collectives is warp-uniform: a branch that only some scenarios need is taken by the whole warp when ANY
 // scenario votes for it and its result is ignored elsewhere (a refactorisation with an unchanged rho reproduces
@@ -554,6 +563,7 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
                                             const f2 nal2, int nvar, f2* sm, float4* cf, bool live, Emit emit) {
     typedef GroupComm<LPS> GC;
     const int gl = cm.gl;
+    MPC_PHASE_MARK(1);
     if (st.scaling > 0) ruiz_scale2<LPS>(cm, s, st.scaling, nvar);
     else {
 #pragma unroll
@@ -563,6 +573,7 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
         s.cs = 1.0f;
     }
     const float thr = (float)(kOsqpInfty * kMinScaling);
+    MPC_PHASE_MARK(2);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         sm[i * LPS + gl] = s.d[i]; sm[(8 + i) * LPS + gl] = s.Ed[i];
@@ -582,6 +593,7 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
     set_rho2<LPS, LOOSE>(sm, gl, rho, rdf, rb);
     PairFactor<LPS> f;
     factorize2<LPS, LOOSE>(cm, s, f, sigma, rdf, rb, sm, cf);
+    MPC_PHASE_MARK(3);
     float nq_s = 0.0f, nq_u = 0.0f;
 #pragma unroll
     for (int i = 0; i < 5; ++i) { amax(nq_s, s.q[i]); amax(nq_u, pmul(s.q[i], sm[(16 + i) * LPS + gl])); }
@@ -607,7 +619,9 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
         SolveResult r;
         r.iters = it;
         r.status = status;
+        MPC_PHASE_MARK(4);
         emit(w, r);
+        MPC_PHASE_MARK(5);
         done = true;
     };
     // one ADMM pass
@@ -898,6 +912,9 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
         asm volatile("pmevent 2;");
 #endif
         if (after_pass()) break;   // phase 2 always ends here: every scenario still open is finished with -2
+#ifdef MPC_PHASE_CLOCK
+        if (iter == 1) MPC_PHASE_MARK(7);
+#endif
         if (phase == 1 || (phase == 0 && iter >= st.max_iter)) {
             // the last pass was a check pass iff check_termination divides max_iter
             const bool checked = phase == 0 && st.check_termination > 0 && (st.max_iter % st.check_termination == 0);

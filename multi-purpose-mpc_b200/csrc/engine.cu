@@ -56,6 +56,7 @@ struct mpc_engine {
     double length = 0.0;
     DevBuf<double> d_wp;      // [13][n_wp]: 12 rows + length_cum
     DevBuf<double> d_border;  // [n_wp][4]
+    DevBuf<double> d_stage_tab;  // [n_wp][kStageTab]: K1's per-waypoint coefficients (PathView::stage_tab)
     std::vector<double> h_wp, h_border;
     bool have_path = false, have_border = false;
     PathView pv{};
@@ -227,6 +228,8 @@ int mpc_engine_set_stream(mpc_engine* h, void* s) {
     return 0;
 }
 
+static int build_stage_table(mpc_engine* h);
+
 int mpc_engine_update_config(mpc_engine* h, const mpc_config* cfg) {
     if (!h || !cfg) return fail(MPC_E_INVALID, "null argument");
     if (cfg->N != h->cfg.N) return fail(MPC_E_INVALID, "N cannot change after creation");
@@ -234,7 +237,7 @@ int mpc_engine_update_config(mpc_engine* h, const mpc_config* cfg) {
     h->cfg = *cfg;
     refresh_params(h);
     drop_graph(h);
-    return 0;
+    return build_stage_table(h);
 }
 
 int mpc_engine_sync(mpc_engine* h) {
@@ -253,6 +256,16 @@ static void bind_path(mpc_engine* h) {
     v.cos_psi = p + 6 * n; v.sin_psi = p + 7 * n; v.cos_ub = p + 8 * n; v.sin_ub = p + 9 * n; v.cos_lb = p + 10 * n;
     v.sin_lb = p + 11 * n; v.length_cum = p + 12 * n;
     v.border = h->d_border.p;
+    v.stage_tab = h->d_stage_tab.p;
+}
+
+// K1's per-waypoint coefficients depend on the path (ds, kappa), v_ref and R: rebuilt by whoever changes one of them
+static int build_stage_table(mpc_engine* h) {
+    if (!h->have_path) return 0;
+    launch_build_stage_table(h->pv, h->mp, h->d_stage_tab.p, h->stream);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 // rows of the grid that the rays of a horizon starting at waypoint w (N waypoints) can touch
@@ -319,6 +332,7 @@ int mpc_set_path(mpc_engine* h, const double* h_wp, const double* h_length_cum, 
     CUDA_OK(cudaMemcpyAsync(h->d_wp.p, h->h_wp.data(), 13 * (size_t)n_wp * sizeof(double), cudaMemcpyHostToDevice,
                             h->stream));
     CUDA_OK(h->d_border.alloc(4 * (size_t)n_wp));
+    CUDA_OK(h->d_stage_tab.alloc(kStageTab * (size_t)n_wp));
     h->have_border = false;
     if (h_border) {
         h->h_border.assign(h_border, h_border + 4 * (size_t)n_wp);
@@ -330,6 +344,7 @@ int mpc_set_path(mpc_engine* h, const double* h_wp, const double* h_length_cum, 
     h->have_path = true;
     bind_path(h);
     drop_graph(h);
+    if (int r = build_stage_table(h)) return r;
     return compute_rowspan(h);
 }
 
@@ -339,8 +354,7 @@ int mpc_set_vref(mpc_engine* h, const double* h_vref, int32_t n_wp) {
     memcpy(&h->h_wp[4 * (size_t)n_wp], h_vref, n_wp * sizeof(double));
     CUDA_OK(cudaMemcpyAsync(h->d_wp.p + 4 * (size_t)n_wp, h_vref, n_wp * sizeof(double), cudaMemcpyHostToDevice,
                             h->stream));
-    CUDA_OK(cudaStreamSynchronize(h->stream));
-    return 0;
+    return build_stage_table(h);  // synchronises
 }
 
 static int apply_obstacles(mpc_engine* h);

@@ -71,6 +71,7 @@ int launch_assemble_solve(int precision, const MpcParams& mp, const AdmmSettings
                           cudaStream_t s, double* rollout_state = nullptr, double Ts = 0.0, const int* order = nullptr,
                           bool prefer_stage = false, const HostIO* host_io = nullptr);
 
+void launch_build_stage_table(const PathView& pv, const MpcParams& mp, double* tab /*[n_wp][kStageTab]*/, cudaStream_t s);
 bool solve_writes_host_io();  // false for the opt-in variants (MPC_ADMM_KERNEL=tm / quad), which only fill device buffers
 void preload_solve_kernels(int precision, int N, int B = 0);
 void preload_pair_kernels(int N);

@@ -405,6 +405,40 @@ def test_host_step_without_copy_nodes(engine_factory, track, monkeypatch, per_sc
                 assert np.array_equal(o[k], od[k]), (mode, k)
 
 
+@pytest.mark.parametrize("precision", [0, 1])
+def test_stage_table_follows_vref_and_weights(engine_factory, track, precision):
+    """K1 reads its per-waypoint coefficients (entries of A_lin, B_lin, uq, q: functions of ds, kappa, v_ref and R) from a
+    table built when the path is set.  Changing v_ref (compute_speed_profile, rp.py:289-354) or R afterwards must give the
+    same step as an engine that was created with them, and a different one from before the change."""
+    import mpc_b200
+    from mpc_b200 import _lib
+    TF = load_golden("teacher_forced.npz")
+    st0 = np.ascontiguousarray(TF["state"][:64].T)
+    v2 = np.clip(track.wp_vref * 0.8 + 0.05, 0.05, None)
+    R2 = [0.2, 0.01]
+
+    a = engine_factory(grid="free", precision=precision)                 # old v_ref and R, then changed in place
+    a.scenarios_init(st0)
+    a.step()
+    before = a.scenarios_read()
+    a.set_vref(v2)
+    a.update_config(R=R2)
+    a.scenarios_init(st0)
+    a.step()
+    oa = a.scenarios_read()
+
+    b = mpc_b200.Engine(precision=precision, R=R2)                         # created with them
+    b.set_path(_lib.path_table(track.wp_x, track.wp_y, track.wp_psi, track.wp_kappa, v2), track.length_cum, track.border, True)
+    b.set_base_grid(track.grid, track.origin, track.res)
+    b.scenarios_init(st0)
+    b.step()
+    ob = b.scenarios_read()
+    b.close()
+    for k in ("state", "control", "u", "iters", "qp_status", "flags"):
+        assert np.array_equal(oa[k], ob[k]), k
+    assert not np.array_equal(before["u"], oa["u"])
+
+
 def test_batch_properties_at_c2_size(engine_factory, track):
     """BASELINE config 2 size (4096 cars): permutation equivariance and replica consistency of a full step."""
     from mpc_b200 import distributed as D
