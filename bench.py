@@ -874,10 +874,11 @@ def main():
             "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * B * 8),
                     "d2h_bytes_per_step": int(6 * B * 8 + 4 * B),
-                    "path": "mpc_step_host on page-locked host buffers, one graph launch per step: the first kernel reads the "
-                            "state from the host buffer over PCIe, the solve kernel's epilogue writes state / u / flags into "
-                            "the host buffers (no staging copies); host wall clock around each of the K synchronous calls, "
-                            "summed" if io_mode_default[0] != "c" else
+                    "path": ("mpc_step_host on page-locked host buffers, one graph launch per step: " +
+                             ("H2D node for the state, then the ray-cast kernel; " if args.workload == "obstacles" else
+                              "the first kernel reads the state from the host buffer over PCIe; ") +
+                             "the solve kernel's epilogue writes state / u / flags into the host buffers (no staging copies); "
+                             "host wall clock around each of the K synchronous calls, summed") if io_mode_default[0] != "c" else
                             "mpc_step_host on page-locked host buffers (H2D + 2 kernels + D2H = one graph launch), host "
                             "wall clock around each of the K synchronous calls, summed",
                     "with_copy_nodes_value": e2e_copy_nodes, "pageable_buffers_value": e2e_pageable},
