@@ -645,8 +645,8 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
         }
         return 0;
     };
-    for (iter = 1; iter <= st.max_iter; ++iter) {
-        T dl[5], ed[3], eb[5];
+    // one ADMM pass; leaves this pass's steps dl (primal), ed / eb (dual) for the checks
+    auto pass = [&](T* dl, T* ed, T* eb) __attribute__((always_inline)) {
         T g[5], td[3], tb[5];
 #pragma unroll
         for (int i = 0; i < 3; ++i) td[i] = rd * rdy[i];
@@ -684,6 +684,25 @@ __device__ __forceinline__ SolveResult admm_solve(Comm& cm, Stage<T>& s, const A
 #pragma unroll
             for (int i = 0; i < 5; ++i) ty[i] += dty[i];
         }
+    };
+    for (iter = 1; iter <= st.max_iter; ++iter) {
+        T dl[5], ed[3], eb[5];
+        // Passes after which nothing happens (no check, no rho adaptation, not the last one) run in a loop of their own: one
+        // straight-line body and one backward branch instead of a round trip through the check code's branches.  Same
+        // passes in the same order; the check lambda would only have decremented the two counters.
+        {
+            int quiet = st.max_iter - iter;
+            if (chk > 0) quiet = min(quiet, chk - 1);
+            if (adp > 0) quiet = min(quiet, adp - 1);
+#pragma unroll 1
+            for (int i = 0; i < quiet; ++i) pass(dl, ed, eb);
+            if (quiet > 0) {
+                iter += quiet;
+                if (chk > 0) chk -= quiet;
+                if (adp > 0) adp -= quiet;
+            }
+        }
+        pass(dl, ed, eb);
         const bool can_check = (--chk == 0), can_adapt = (--adp == 0);
         if (can_check) chk = st.check_termination;
         if (can_adapt) adp = st.adaptive_rho_interval;

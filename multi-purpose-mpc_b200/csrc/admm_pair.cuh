@@ -904,6 +904,22 @@ __device__ __forceinline__ void admm_solve2(const GroupComm<LPS>& cm, Stage2& s,
         return false;
     };
     for (iter = 1;; ++iter) {
+        // Passes after which nothing happens (no check, no rho adaptation, not the last one) run in a loop of their own:
+        // one straight-line body and one backward branch, instead of a round trip through the check code's branches
+        // (which ptxas lays out far from the pass and which showed up as instruction-fetch stalls).  Same passes, same
+        // order; `after_pass` would only have decremented the two counters.
+        if (phase == 0 && iter > 1) {
+            int quiet = st.max_iter - iter;
+            if (chk > 0) quiet = min(quiet, chk - 1);
+            if (adp > 0) quiet = min(quiet, adp - 1);
+#pragma unroll 1
+            for (int i = 0; i < quiet; ++i) pass(false, false);
+            if (quiet > 0) {
+                iter += quiet;
+                if (chk > 0) chk -= quiet;
+                if (adp > 0) adp -= quiet;
+            }
+        }
 #ifdef MPC_QUAD_MARK   // PMTRIG markers around the pass (tools/sass_pass.py)
         asm volatile("pmevent 1;");
 #endif

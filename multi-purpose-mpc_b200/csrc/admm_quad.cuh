@@ -1062,6 +1062,19 @@ __device__ __forceinline__ void admm_solve4(const QuadComm<LPS>& cm, Stage2 (&s)
 #define QUAD_MARK(n)
 #endif
     for (iter = 1;; ++iter) {
+        // passes after which nothing happens run in a loop of their own (see admm_pair.cuh)
+        if (phase == 0 && iter > 1) {
+            int quiet = st.max_iter - iter;
+            if (chk > 0) quiet = min(quiet, chk - 1);
+            if (adp > 0) quiet = min(quiet, adp - 1);
+#pragma unroll 1
+            for (int i = 0; i < quiet; ++i) pass(false, false);
+            if (quiet > 0) {
+                iter += quiet;
+                if (chk > 0) chk -= quiet;
+                if (adp > 0) adp -= quiet;
+            }
+        }
         QUAD_MARK(1);
         if (phase == 0) pass(iter == 1, chk == 1 || iter >= st.max_iter);
         QUAD_MARK(2);
