@@ -810,24 +810,31 @@ def main():
         for _ in range(args.warmup):
             eng.step_host(hs, hu, hf)
         barrier()
-        s0 = eng.scenarios_read() if args.steps > RESTART else None
-        t_acc = 0.0
-        for k in range(args.steps):
-            if k and k % RESTART == 0:  # long runs only; not part of a step, so outside the clock
-                hs[:] = s0["state"]
-                eng.scenarios_set_state(None, s0["control"], s0["infeas"])
-            t0 = time.perf_counter()
-            eng.step_host(hs, hu, hf)  # synchronous: returns when the results are in the host buffers
-            t_acc += time.perf_counter() - t0
-        barrier()
-        dt = D.max_over_ranks(t_acc)
+        # K steps are a few milliseconds of host wall clock, so one scheduler hiccup on the host would decide the number:
+        # the same K steps (the fleet is put back to its post-warm-up state first, outside the clock) are timed
+        # E2E_REPEATS times and the median is reported, with every repetition's value next to it.
+        s0 = eng.scenarios_read()
+        vals = []
+        for rep in range(E2E_REPEATS):
+            t_acc = 0.0
+            for k in range(args.steps):
+                if k % RESTART == 0 and (k or rep):  # not part of a step, so outside the clock
+                    hs[:] = s0["state"]
+                    eng.scenarios_set_state(None, s0["control"], s0["infeas"])
+                    eng.scenarios_set_flags(s0["flags"])  # set_state clears them: retired scenarios stay retired
+                t0 = time.perf_counter()
+                eng.step_host(hs, hu, hf)  # synchronous: returns when the results are in the host buffers
+                t_acc += time.perf_counter() - t0
+            barrier()
+            vals.append(Bg * args.steps / D.max_over_ranks(t_acc))
         chk = np.array(hu, copy=True)  # the results are read on the host
         eng.close()
-        return Bg * args.steps / dt, chk
+        return float(np.median(vals)), chk, vals
+    E2E_REPEATS = 5
     io_mode_default = os.environ.get("MPC_HOST_IO", "kernel")
-    e2e_value, e2e_chk = time_e2e(True, io_mode_default)
-    e2e_copy_nodes, e2e_chk3 = time_e2e(True, "copy")
-    e2e_pageable, e2e_chk2 = time_e2e(False, io_mode_default)
+    e2e_value, e2e_chk, e2e_all = time_e2e(True, io_mode_default)
+    e2e_copy_nodes, e2e_chk3, _ = time_e2e(True, "copy")
+    e2e_pageable, e2e_chk2, _ = time_e2e(False, io_mode_default)
     os.environ["MPC_HOST_IO"] = io_mode_default
     assert np.array_equal(e2e_chk, e2e_chk2, equal_nan=True) and np.array_equal(e2e_chk, e2e_chk3, equal_nan=True) and \
         np.nansum(np.abs(e2e_chk)) > 0, "step_host paths (kernel-side host I/O, copy nodes, pageable) disagree"
@@ -881,6 +888,7 @@ def main():
                              "host wall clock around each of the K synchronous calls, summed") if io_mode_default[0] != "c" else
                             "mpc_step_host on page-locked host buffers (H2D + 2 kernels + D2H = one graph launch), host "
                             "wall clock around each of the K synchronous calls, summed",
+                    "repeats": E2E_REPEATS, "repeat_values": e2e_all, "statistic": "median of the repeats, each exactly K steps",
                     "with_copy_nodes_value": e2e_copy_nodes, "pageable_buffers_value": e2e_pageable},
             "gpu_launches": int(launches),
             "kernel_ms": kernel_ms,
